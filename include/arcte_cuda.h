@@ -1,0 +1,176 @@
+/*
+ * arcte_cuda.h -- C ABI of the B200-native ARCTE feature extractor.
+ *
+ * The reference (MKLab-ITI/reveal-graph-embedding) is pure Python and has no FFI
+ * for this path; the boundary is the Python call
+ *     arcte(adjacency_matrix, rho, epsilon, number_of_threads)
+ *         reveal_graph_embedding/embedding/arcte/arcte.py:591
+ * and, one level down, the raw-array hand-off its workers receive
+ *     arcte_worker(iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon)
+ *         reveal_graph_embedding/embedding/arcte/arcte.py:279-286
+ * Every entry point below names the reference code it replaces.  A maintainer
+ * binds them with ctypes; no torch types appear here.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative ARCTE_E_* code on
+ *     failure; arcte_cuda_last_error() then returns a message (thread local).
+ *   - "host" pointers are ordinary process memory (pinned or not); "dev"
+ *     pointers are CUDA device pointers on the context's device.
+ *   - one context drives one GPU and is not re-entrant; calls block until the
+ *     result is complete (ctypes releases the GIL around them).
+ *   - the adjacency CSR must be canonical (sorted column indices, no
+ *     duplicates) with positive weights, which is what scipy hands the
+ *     reference after csr_matrix()/sort_indices() (transition.py:52,65).
+ */
+#ifndef ARCTE_CUDA_H
+#define ARCTE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct arcte_cuda_ctx arcte_cuda_ctx;
+
+enum {
+    ARCTE_OK = 0,
+    ARCTE_E_CUDA = -1,      /* a CUDA runtime call failed                          */
+    ARCTE_E_ARG = -2,       /* bad argument / call order                            */
+    ARCTE_E_NOMEM = -3,     /* not enough device memory for the requested graph     */
+    ARCTE_E_OVERFLOW = -4   /* a per-seed queue could not be grown any further      */
+};
+
+/* Push rules: which similarity.py driver + push.py rule the engine runs. */
+enum {
+    ARCTE_RULE_ABSORBING = 0, /* fast_approximate_cumulative_pagerank_difference, similarity.py:149;
+                                 cumulative_pagerank_difference_limit_push, push.py:41   (arcte, arcte.py:591) */
+    ARCTE_RULE_PAGERANK = 1,  /* fast_approximate_personalized_pagerank, similarity.py:11;
+                                 pagerank_limit_push, push.py:4          (arcte_with_pagerank, arcte.py:491) */
+    ARCTE_RULE_LAZY = 2       /* lazy_approximate_personalized_pagerank, similarity.py:66;
+                                 pagerank_lazy_push, push.py:20     (arcte_with_lazy_pagerank, arcte.py:391) */
+};
+
+/* Counters and device timings of the last arcte_cuda_extract/assemble on this context. */
+typedef struct arcte_cuda_stats {
+    int64_t n_seeds_total;   /* seeds selected on the graph (arcte.py:614-617)              */
+    int64_t n_seeds_shard;   /* seeds this context processed                                 */
+    int64_t pushes;          /* push operations (similarity.py return value, summed)          */
+    int64_t edge_touches;    /* sum of deg(u) over pushes                                     */
+    int64_t enqueues;        /* FIFO appends                                                  */
+    int64_t max_queue;       /* longest live FIFO of any seed                                 */
+    int64_t support;         /* sum over seeds of |{x : s[x] != 0}|                           */
+    int64_t touched;         /* sum over seeds of nodes whose s or r left zero                */
+    int64_t seed_degree;     /* sum over seeds of deg(seed)                                   */
+    int64_t members;         /* sum over emitted seeds of community size                      */
+    int64_t emitted;         /* seeds that emitted a community (arcte.py:370)                 */
+    int64_t retries;         /* seeds re-run with a larger FIFO                               */
+    int64_t n_slots;         /* concurrent per-warp walk states used                          */
+    int64_t launches;        /* kernels launched by the last build/extract/assemble calls     */
+    double ms_transition;    /* K1: degrees + row normalisation                               */
+    double ms_seeds;         /* K2: seed selection/ordering + epsilon-effective               */
+    double ms_push;          /* K3+K4: fused push / threshold / compaction kernel             */
+    double ms_assemble;      /* K5: pack, transpose, splice                                    */
+    double alg_bytes_push;   /* SURVEY 8(d) algorithmic bytes of the push kernel              */
+} arcte_cuda_stats;
+
+/* -- lifetime ------------------------------------------------------------- */
+int arcte_cuda_device_count(int *count); /* CUDA devices visible to this process */
+int arcte_cuda_create(arcte_cuda_ctx **out, int device_id);
+void arcte_cuda_destroy(arcte_cuda_ctx *ctx);
+const char *arcte_cuda_last_error(void);
+/* Tuning knobs (0 keeps the default): concurrent walk states per SM, per-seed FIFO
+   capacity in entries, fraction of free HBM the walk states may take (percent), initial
+   capacity of the member buffer in entries.  FIFO rings and the member buffer grow on
+   demand (affected seeds are re-run), so small values are safe, only slower. */
+int arcte_cuda_configure(arcte_cuda_ctx *ctx, int warps_per_sm, int64_t queue_capacity,
+                         int mem_percent, int64_t member_capacity);
+
+/* -- a11 + a1: graph upload and transition build --------------------------- */
+/* Replaces the pickled (indices, indptr, data) hand-off of arcte.py:657-665 and
+   get_natural_random_walk_matrix, eps_randomwalk/transition.py:43-68.  Copies the
+   host CSR of the ADJACENCY matrix to the device and runs K1. */
+int arcte_cuda_set_graph(arcte_cuda_ctx *ctx, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                         const int32_t *host_indices, const double *host_data);
+/* Re-runs K1 (degrees, row normalisation) and K2a (seed selection) on the adjacency
+   already resident in HBM -- the timed "inputs resident" form of the above. */
+int arcte_cuda_build_transition(arcte_cuda_ctx *ctx);
+/* W.data (nnz), out_degree (n), in_degree (n) to host: transition.py:99 return value. */
+int arcte_cuda_get_transition(arcte_cuda_ctx *ctx, double *host_w, double *host_d_out,
+                              double *host_d_in);
+
+/* The same hand-off one level lower: the caller already holds W, out_degree and
+   in_degree (exactly the raw arrays arcte_worker receives, arcte.py:279-286) and
+   uploads them as they are; K1 is skipped, the seed list is still derived on the GPU. */
+int arcte_cuda_set_transition(arcte_cuda_ctx *ctx, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                              const int32_t *host_indices, const double *host_w,
+                              const double *host_d_out, const double *host_d_in);
+
+/* -- a2: seed selection ---------------------------------------------------- */
+/* arcte.py:610-617: nodes whose binarised column count is > 1, count-descending. */
+int arcte_cuda_get_seed_count(arcte_cuda_ctx *ctx, int64_t *n_seeds);
+int arcte_cuda_get_seeds(arcte_cuda_ctx *ctx, int64_t *host_seeds);
+/* Replace the seed list by the caller's `iterate_nodes` (arcte_worker's first argument). */
+int arcte_cuda_set_seeds(arcte_cuda_ctx *ctx, int64_t n_seeds, const int64_t *host_seeds);
+
+/* -- a4: epsilon-effective -------------------------------------------------- */
+/* calculate_epsilon_effective, arcte.py:26-50, for the given seed nodes. */
+int arcte_cuda_epsilon_effective(arcte_cuda_ctx *ctx, double epsilon, int64_t n_seeds,
+                                 const int64_t *host_seeds, double *host_eps_out);
+
+/* -- a5-a7: operator seam, one seed ----------------------------------------- */
+/* Same contract as similarity.py:149/:11/:66 on zeroed s and r: fills dense
+   host_s[n], host_r[n] and the push count.  `rho` is used as given (the lazy
+   worker passes lazy_rho, arcte.py:109); laziness factor is the reference's 0.5. */
+int arcte_cuda_push(arcte_cuda_ctx *ctx, int rule, int64_t seed, double rho, double eps_eff,
+                    double *host_s, double *host_r, int64_t *n_push);
+
+/* -- a3 + a4-a8: extraction over a shard of the seed list -------------------- */
+/* arcte_worker (arcte.py:279-388) for seed-list positions shard_rank,
+   shard_rank + shard_count, ... (roundrobin_chunks, arcte.py:19-23).
+   host_eps_override: NULL, or one epsilon-effective per GLOBAL seed-list position
+   (parity seam).  Results stay on the device as segments. */
+int arcte_cuda_extract(arcte_cuda_ctx *ctx, int rule, double rho, double epsilon, int shard_rank,
+                       int shard_count, const double *host_eps_override, int64_t *n_segments,
+                       int64_t *n_members);
+/* Segment k: seed node seg_seed[k], seg_count[k] members at members[seg_offset[k] ...]. */
+int arcte_cuda_get_segments(arcte_cuda_ctx *ctx, int32_t *host_seg_seed, int32_t *host_seg_count,
+                            int64_t *host_seg_offset, int32_t *host_members);
+/* Device-resident views of the same four arrays (for an NCCL all-gather by the caller). */
+int arcte_cuda_segments_device(arcte_cuda_ctx *ctx, const int32_t **dev_seg_seed,
+                               const int32_t **dev_seg_count, const int64_t **dev_seg_offset,
+                               const int32_t **dev_members);
+
+/* Copies the same four arrays into caller-owned DEVICE buffers (e.g. tensors a
+   collective library will send); sizes as returned by arcte_cuda_extract. */
+int arcte_cuda_export_segments(arcte_cuda_ctx *ctx, int32_t *dev_seg_seed, int32_t *dev_seg_count,
+                               int64_t *dev_seg_offset, int32_t *dev_members);
+
+/* -- a9 + a10: assembly ------------------------------------------------------ */
+/* arcte.py:379-386 and :670-688: features = hstack([I + pattern(A), local]) as a
+   canonical n x 2n CSR.  Parts are segment sets (this context's own and/or those
+   gathered from other GPUs), given as DEVICE pointers readable from this device.
+   Parts living on another GPU of the box are first copied over NVLink (peer copy).
+   n_parts == 0 assembles the context's own last extraction. */
+int arcte_cuda_assemble(arcte_cuda_ctx *ctx, int n_parts, const int64_t *part_n_segments,
+                        const int64_t *part_n_members, const int32_t *const *dev_seg_seed, const int32_t *const *dev_seg_count,
+                        const int64_t *const *dev_seg_offset, const int32_t *const *dev_members,
+                        int64_t *nnz_out);
+int arcte_cuda_get_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *host_indices,
+                            double *host_data);
+
+/* -- measurement helpers ------------------------------------------------------ */
+/* CUDA events on the context's own stream (the stream every kernel of this library is
+   launched on), so a caller can time a whole step on the device. */
+int arcte_cuda_timer_start(arcte_cuda_ctx *ctx);
+int arcte_cuda_timer_stop(arcte_cuda_ctx *ctx, double *elapsed_ms);
+/* Overwrites a scratch buffer larger than the 126 MB L2 (cold-cache timing). */
+int arcte_cuda_flush_l2(arcte_cuda_ctx *ctx);
+
+/* -- stats ------------------------------------------------------------------- */
+int arcte_cuda_get_stats(arcte_cuda_ctx *ctx, arcte_cuda_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCTE_CUDA_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libarcte_cuda.so (C ABI: include/arcte_cuda.h).
+
+This is the only place the shared library is loaded.  It fails loudly: a missing
+library, a missing symbol or a non-zero status raises -- nothing here or above
+falls back to a CPU implementation.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarcte_cuda.so")
+
+RULE_ABSORBING, RULE_PAGERANK, RULE_LAZY = 0, 1, 2
+
+# every symbol include/arcte_cuda.h declares (tests/test_abi.py checks the two lists agree)
+SYMBOLS = [
+    "arcte_cuda_device_count", "arcte_cuda_create", "arcte_cuda_destroy", "arcte_cuda_last_error", "arcte_cuda_configure",
+    "arcte_cuda_set_graph", "arcte_cuda_set_transition", "arcte_cuda_set_seeds", "arcte_cuda_build_transition", "arcte_cuda_get_transition",
+    "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
+    "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
+    "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_get_features",
+    "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "n_seeds_total", "n_seeds_shard", "pushes", "edge_touches", "enqueues", "max_queue",
+        "support", "touched", "seed_degree", "members", "emitted", "retries", "n_slots",
+        "launches")] + [(k, C.c_double) for k in (
+            "ms_transition", "ms_seeds", "ms_push", "ms_assemble", "alg_bytes_push")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ArcteCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the library once; raise if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ArcteCudaError(
+                "libarcte_cuda.so is not built (%s). Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C reveal_graph_embedding_b200/csrc`. There is no CPU fallback."
+                % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for s in SYMBOLS:
+            getattr(L, s)  # AttributeError if the ABI drifted
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+        L.arcte_cuda_last_error.restype = C.c_char_p
+        L.arcte_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.arcte_cuda_create.argtypes = [C.POINTER(vp), i32]
+        L.arcte_cuda_destroy.argtypes = [vp]
+        L.arcte_cuda_destroy.restype = None
+        L.arcte_cuda_configure.argtypes = [vp, i32, i64, i32, i64]
+        L.arcte_cuda_set_graph.argtypes = [vp, i64, i64, vp, vp, vp]
+        L.arcte_cuda_set_transition.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
+        L.arcte_cuda_set_seeds.argtypes = [vp, i64, vp]
+        L.arcte_cuda_build_transition.argtypes = [vp]
+        L.arcte_cuda_get_transition.argtypes = [vp, vp, vp, vp]
+        L.arcte_cuda_get_seed_count.argtypes = [vp, C.POINTER(i64)]
+        L.arcte_cuda_get_seeds.argtypes = [vp, vp]
+        L.arcte_cuda_epsilon_effective.argtypes = [vp, dbl, i64, vp, vp]
+        L.arcte_cuda_push.argtypes = [vp, i32, i64, dbl, dbl, vp, vp, C.POINTER(i64)]
+        L.arcte_cuda_extract.argtypes = [vp, i32, dbl, dbl, i32, i32, vp, C.POINTER(i64), C.POINTER(i64)]
+        L.arcte_cuda_get_segments.argtypes = [vp, vp, vp, vp, vp]
+        L.arcte_cuda_segments_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.arcte_cuda_export_segments.argtypes = [vp, vp, vp, vp, vp]
+        L.arcte_cuda_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+        L.arcte_cuda_get_features.argtypes = [vp, vp, vp, vp]
+        L.arcte_cuda_timer_start.argtypes = [vp]
+        L.arcte_cuda_timer_stop.argtypes = [vp, C.POINTER(dbl)]
+        L.arcte_cuda_flush_l2.argtypes = [vp]
+        L.arcte_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        for s in SYMBOLS:
+            if s not in ("arcte_cuda_last_error", "arcte_cuda_destroy"):
+                getattr(L, s).restype = C.c_int
+        _lib = L
+        return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().arcte_cuda_last_error()
+        raise ArcteCudaError("libarcte_cuda status %d: %s" % (rc, (msg or b"").decode("utf-8", "replace")))
+
+
+def ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)

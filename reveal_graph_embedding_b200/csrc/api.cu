@@ -1,0 +1,480 @@
+// api.cu -- the extern "C" boundary declared in include/arcte_cuda.h.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace arcte {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int dev_reserve(DevBuf &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.bytes >= bytes) return ARCTE_OK;
+    if (b.p) {
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        b.p = nullptr;
+        return e == cudaErrorMemoryAllocation ? ARCTE_E_NOMEM : ARCTE_E_CUDA;
+    }
+    b.bytes = bytes;
+    return ARCTE_OK;
+}
+
+void dev_free(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+// implemented in the other translation units
+int build_transition(arcte_cuda_ctx *c);
+int select_seeds(arcte_cuda_ctx *c);
+int count_columns(arcte_cuda_ctx *c);
+int compute_eps_effective(arcte_cuda_ctx *c, double epsilon, const int32_t *dev_seeds, int64_t n_seeds,
+                          double *dev_eps_out);
+int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int shard_rank, int shard_count,
+                  const double *host_eps_override);
+int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double eps_eff, double *host_s,
+                double *host_r, int64_t *n_push);
+struct SegPart {
+    int64_t n_segments;
+    const int32_t *seg_seed;
+    const int32_t *seg_count;
+    const int64_t *seg_offset;
+    const int32_t *members;
+};
+int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts);
+
+}  // namespace arcte
+
+using namespace arcte;
+
+#define CHECK_CTX(ctx)                                   \
+    do {                                                 \
+        if (!(ctx)) {                                    \
+            set_error("null context");                   \
+            return ARCTE_E_ARG;                          \
+        }                                                \
+        ARCTE_CUDA_TRY(cudaSetDevice((ctx)->device));    \
+    } while (0)
+
+extern "C" {
+
+const char *arcte_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int arcte_cuda_device_count(int *count)
+{
+    if (!count) { set_error("device_count: null pointer"); return ARCTE_E_ARG; }
+    *count = 0;
+    ARCTE_CUDA_TRY(cudaGetDeviceCount(count));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_create(arcte_cuda_ctx **out, int device_id)
+{
+    if (!out) { set_error("create: null out pointer"); return ARCTE_E_ARG; }
+    *out = nullptr;
+    int count = 0;
+    ARCTE_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device_id < 0 || device_id >= count) {
+        set_error("create: device " + std::to_string(device_id) + " not present (" + std::to_string(count) +
+                  " CUDA devices)");
+        return ARCTE_E_ARG;
+    }
+    ARCTE_CUDA_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    ARCTE_CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) {
+        set_error(std::string("create: this library is built for sm_100a only; device is ") + prop.name +
+                  " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+        return ARCTE_E_ARG;
+    }
+    arcte_cuda_ctx *c = new arcte_cuda_ctx();
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    ARCTE_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->ev0));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->ev1));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->tm0));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->tm1));
+    *out = c;
+    return ARCTE_OK;
+}
+
+void arcte_cuda_destroy(arcte_cuda_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->seeds,
+                      &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
+                      &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->counters, &c->out_indptr,
+                      &c->out_indices, &c->out_data};
+    for (DevBuf *b : bufs) dev_free(*b);
+    for (DevBuf &b : c->scratch) dev_free(b);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->tm0);
+    cudaEventDestroy(c->tm1);
+    dev_free(c->l2_flush);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int arcte_cuda_configure(arcte_cuda_ctx *c, int warps_per_sm, int64_t queue_capacity, int mem_percent,
+                         int64_t member_capacity)
+{
+    CHECK_CTX(c);
+    if (warps_per_sm < 0 || warps_per_sm > 64 || queue_capacity < 0 || mem_percent < 0 || mem_percent > 95 ||
+        member_capacity < 0) {
+        set_error("configure: argument out of range");
+        return ARCTE_E_ARG;
+    }
+    c->warps_per_sm = warps_per_sm;
+    c->queue_cap_cfg = queue_capacity;
+    c->mem_percent = mem_percent;
+    c->member_cap_cfg = member_capacity;
+    dev_free(c->members);  // re-created with the new capacity at the next extract
+    c->member_cap = 0;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_set_graph(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                         const int32_t *host_indices, const double *host_data);
+
+static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                            const int32_t *host_indices)
+{
+    if (n <= 0 || nnz < 0 || !host_indptr || (nnz > 0 && !host_indices)) {
+        set_error("graph upload: bad arguments");
+        return ARCTE_E_ARG;
+    }
+    if (n >= (int64_t(1) << 30)) { set_error("graph upload: n must be < 2^30"); return ARCTE_E_ARG; }
+    if (host_indptr[0] != 0 || host_indptr[n] != nnz) {
+        set_error("graph upload: indptr[0] must be 0 and indptr[n] must equal nnz");
+        return ARCTE_E_ARG;
+    }
+    c->have_graph = c->have_transition = c->have_segments = c->have_features = false;
+    if (n != c->n) {
+        // slot geometry depends on n: drop the pool (re-created lazily)
+        dev_free(c->slots.sr);
+        dev_free(c->slots.touched);
+        dev_free(c->slots.queue);
+        c->slots = SlotPool();
+    }
+    c->n = n;
+    c->nnz = nnz;
+    c->stats = arcte_cuda_stats();
+    ARCTE_TRY(dev_reserve(c->indptr, sizeof(int64_t) * (size_t)(n + 1)));
+    ARCTE_TRY(dev_reserve(c->indices, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->indptr.p, host_indptr, sizeof(int64_t) * (size_t)(n + 1),
+                                   cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->indices.p, host_indices, sizeof(int32_t) * (size_t)nnz,
+                                       cudaMemcpyHostToDevice, c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_set_transition(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                              const int32_t *host_indices, const double *host_w, const double *host_d_out,
+                              const double *host_d_in)
+{
+    CHECK_CTX(c);
+    if (!host_d_out || !host_d_in || (nnz > 0 && !host_w)) { set_error("set_transition: null array"); return ARCTE_E_ARG; }
+    ARCTE_TRY(upload_structure(c, n, nnz, host_indptr, host_indices));
+    ARCTE_TRY(dev_reserve(c->w, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    ARCTE_TRY(dev_reserve(c->d_out, sizeof(double) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->d_in, sizeof(double) * (size_t)n));
+    if (nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->w.p, host_w, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->d_out.p, host_d_out, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->d_in.p, host_d_in, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->have_graph = true;       // structure resident (adjacency weights are not: K1 cannot be re-run)
+    dev_free(c->adj);
+    ARCTE_TRY(count_columns(c));
+    c->have_transition = true;
+    return select_seeds(c);
+}
+
+int arcte_cuda_set_seeds(arcte_cuda_ctx *c, int64_t n_seeds, const int64_t *host_seeds)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition) { set_error("set_seeds: no graph"); return ARCTE_E_ARG; }
+    if (n_seeds < 0 || n_seeds > c->n || (n_seeds > 0 && !host_seeds)) { set_error("set_seeds: bad arguments"); return ARCTE_E_ARG; }
+    std::vector<int32_t> tmp((size_t)n_seeds);
+    for (int64_t i = 0; i < n_seeds; ++i) {
+        if (host_seeds[i] < 0 || host_seeds[i] >= c->n) { set_error("set_seeds: seed out of range"); return ARCTE_E_ARG; }
+        tmp[(size_t)i] = (int32_t)host_seeds[i];
+    }
+    if (n_seeds > 0) {
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->seeds.p, tmp.data(), sizeof(int32_t) * (size_t)n_seeds, cudaMemcpyHostToDevice, c->stream));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    c->n_seeds = n_seeds;
+    c->stats.n_seeds_total = n_seeds;
+    c->have_segments = c->have_features = false;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_set_graph(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
+                         const int32_t *host_indices, const double *host_data)
+{
+    CHECK_CTX(c);
+    if (nnz > 0 && !host_data) { set_error("set_graph: null data"); return ARCTE_E_ARG; }
+    ARCTE_TRY(upload_structure(c, n, nnz, host_indptr, host_indices));
+    ARCTE_TRY(dev_reserve(c->adj, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->adj.p, host_data, sizeof(double) * (size_t)nnz,
+                                       cudaMemcpyHostToDevice, c->stream));
+    c->have_graph = true;
+    return build_transition(c);
+}
+
+int arcte_cuda_build_transition(arcte_cuda_ctx *c)
+{
+    CHECK_CTX(c);
+    if (!c->have_graph || !c->adj.p) { set_error("build_transition: adjacency weights not resident"); return ARCTE_E_ARG; }
+    return build_transition(c);
+}
+
+int arcte_cuda_get_transition(arcte_cuda_ctx *c, double *host_w, double *host_d_out, double *host_d_in)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition) { set_error("get_transition: nothing built"); return ARCTE_E_ARG; }
+    if (host_w && c->nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_w, c->w.p, sizeof(double) * (size_t)c->nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (host_d_out)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_d_out, c->d_out.p, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (host_d_in)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_d_in, c->d_in.p, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_seed_count(arcte_cuda_ctx *c, int64_t *n_seeds)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition || !n_seeds) { set_error("get_seed_count: no graph"); return ARCTE_E_ARG; }
+    *n_seeds = c->n_seeds;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_seeds(arcte_cuda_ctx *c, int64_t *host_seeds)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition || !host_seeds) { set_error("get_seeds: no graph"); return ARCTE_E_ARG; }
+    std::vector<int32_t> tmp((size_t)c->n_seeds);
+    if (c->n_seeds > 0) {
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->seeds.p, sizeof(int32_t) * (size_t)c->n_seeds,
+                                       cudaMemcpyDeviceToHost, c->stream));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    for (int64_t i = 0; i < c->n_seeds; ++i) host_seeds[i] = tmp[(size_t)i];
+    return ARCTE_OK;
+}
+
+int arcte_cuda_epsilon_effective(arcte_cuda_ctx *c, double epsilon, int64_t n_seeds, const int64_t *host_seeds,
+                                 double *host_eps_out)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition) { set_error("epsilon_effective: no graph"); return ARCTE_E_ARG; }
+    if (n_seeds <= 0) return ARCTE_OK;
+    std::vector<int32_t> tmp((size_t)n_seeds);
+    for (int64_t i = 0; i < n_seeds; ++i) {
+        if (host_seeds[i] < 0 || host_seeds[i] >= c->n) { set_error("epsilon_effective: seed out of range"); return ARCTE_E_ARG; }
+        tmp[(size_t)i] = (int32_t)host_seeds[i];
+    }
+    ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * (size_t)n_seeds));
+    ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * (size_t)n_seeds));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[0].p, tmp.data(), sizeof(int32_t) * (size_t)n_seeds,
+                                   cudaMemcpyHostToDevice, c->stream));
+    ARCTE_TRY(compute_eps_effective(c, epsilon, c->scratch[0].as<int32_t>(), n_seeds, c->scratch[2].as<double>()));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_eps_out, c->scratch[2].p, sizeof(double) * (size_t)n_seeds,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_push(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double eps_eff, double *host_s,
+                    double *host_r, int64_t *n_push)
+{
+    CHECK_CTX(c);
+    if (!host_s || !host_r) { set_error("push: null output"); return ARCTE_E_ARG; }
+    return push_single(c, rule, seed, rho, eps_eff, host_s, host_r, n_push);
+}
+
+int arcte_cuda_extract(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int shard_rank, int shard_count,
+                       const double *host_eps_override, int64_t *n_segments, int64_t *n_members)
+{
+    CHECK_CTX(c);
+    if (rule < 0 || rule > 2) { set_error("extract: unknown rule"); return ARCTE_E_ARG; }
+    ARCTE_TRY(extract_shard(c, rule, rho, epsilon, shard_rank, shard_count, host_eps_override));
+    if (n_segments) *n_segments = c->n_segments;
+    if (n_members) *n_members = c->n_members;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_segments(arcte_cuda_ctx *c, int32_t *host_seg_seed, int32_t *host_seg_count,
+                            int64_t *host_seg_offset, int32_t *host_members)
+{
+    CHECK_CTX(c);
+    if (!c->have_segments) { set_error("get_segments: call extract first"); return ARCTE_E_ARG; }
+    const size_t S = (size_t)c->n_segments;
+    if (S > 0) {
+        if (host_seg_seed) ARCTE_CUDA_TRY(cudaMemcpyAsync(host_seg_seed, c->work_seed.p, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, c->stream));
+        if (host_seg_count) ARCTE_CUDA_TRY(cudaMemcpyAsync(host_seg_count, c->seg_count.p, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, c->stream));
+        if (host_seg_offset) ARCTE_CUDA_TRY(cudaMemcpyAsync(host_seg_offset, c->seg_offset.p, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (host_members && c->n_members > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_members, c->members.p, sizeof(int32_t) * (size_t)c->n_members, cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_segments_device(arcte_cuda_ctx *c, const int32_t **dev_seg_seed, const int32_t **dev_seg_count,
+                               const int64_t **dev_seg_offset, const int32_t **dev_members)
+{
+    CHECK_CTX(c);
+    if (!c->have_segments) { set_error("segments_device: call extract first"); return ARCTE_E_ARG; }
+    if (dev_seg_seed) *dev_seg_seed = c->work_seed.as<int32_t>();
+    if (dev_seg_count) *dev_seg_count = c->seg_count.as<int32_t>();
+    if (dev_seg_offset) *dev_seg_offset = c->seg_offset.as<int64_t>();
+    if (dev_members) *dev_members = c->members.as<int32_t>();
+    return ARCTE_OK;
+}
+
+int arcte_cuda_export_segments(arcte_cuda_ctx *c, int32_t *dev_seg_seed, int32_t *dev_seg_count,
+                               int64_t *dev_seg_offset, int32_t *dev_members)
+{
+    CHECK_CTX(c);
+    if (!c->have_segments) { set_error("export_segments: call extract first"); return ARCTE_E_ARG; }
+    const size_t S = (size_t)c->n_segments, M = (size_t)c->n_members;
+    if (S > 0) {
+        if (dev_seg_seed) ARCTE_CUDA_TRY(cudaMemcpyAsync(dev_seg_seed, c->work_seed.p, sizeof(int32_t) * S, cudaMemcpyDeviceToDevice, c->stream));
+        if (dev_seg_count) ARCTE_CUDA_TRY(cudaMemcpyAsync(dev_seg_count, c->seg_count.p, sizeof(int32_t) * S, cudaMemcpyDeviceToDevice, c->stream));
+        if (dev_seg_offset) ARCTE_CUDA_TRY(cudaMemcpyAsync(dev_seg_offset, c->seg_offset.p, sizeof(int64_t) * S, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (dev_members && M > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(dev_members, c->members.p, sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+// If `p` lives on another device, stage `bytes` of it into `stage` on this context's
+// device (peer DMA over NVLink) and return the local copy.
+static int localise(arcte_cuda_ctx *c, const void *p, size_t bytes, DevBuf &stage, const void **out)
+{
+    *out = p;
+    if (bytes == 0 || p == nullptr) return ARCTE_OK;
+    cudaPointerAttributes at;
+    ARCTE_CUDA_TRY(cudaPointerGetAttributes(&at, p));
+    if (at.type == cudaMemoryTypeDevice && at.device == c->device) return ARCTE_OK;
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+        set_error("assemble: part pointers must be device pointers");
+        return ARCTE_E_ARG;
+    }
+    ARCTE_TRY(dev_reserve(stage, bytes));
+    ARCTE_CUDA_TRY(cudaMemcpyPeerAsync(stage.p, c->device, p, at.device, bytes, c->stream));
+    *out = stage.p;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_assemble(arcte_cuda_ctx *c, int n_parts, const int64_t *part_n_segments,
+                        const int64_t *part_n_members, const int32_t *const *dev_seg_seed,
+                        const int32_t *const *dev_seg_count, const int64_t *const *dev_seg_offset,
+                        const int32_t *const *dev_members, int64_t *nnz_out)
+{
+    CHECK_CTX(c);
+    std::vector<SegPart> parts;
+    std::vector<DevBuf> stage;
+    int rc = ARCTE_OK;
+    if (n_parts == 0) {
+        if (!c->have_segments) { set_error("assemble: call extract first"); return ARCTE_E_ARG; }
+        parts.push_back(SegPart{c->n_segments, c->work_seed.as<int32_t>(), c->seg_count.as<int32_t>(),
+                                c->seg_offset.as<int64_t>(), c->members.as<int32_t>()});
+    } else {
+        if (n_parts < 0 || !part_n_segments || !part_n_members || !dev_seg_seed || !dev_seg_count ||
+            !dev_seg_offset || !dev_members) {
+            set_error("assemble: bad part arrays");
+            return ARCTE_E_ARG;
+        }
+        stage.resize((size_t)n_parts * 4);
+        for (int p = 0; p < n_parts && rc == ARCTE_OK; ++p) {
+            const size_t S = (size_t)part_n_segments[p], M = (size_t)part_n_members[p];
+            const void *a = nullptr, *b = nullptr, *d = nullptr, *e = nullptr;
+            rc = localise(c, dev_seg_seed[p], S * sizeof(int32_t), stage[(size_t)p * 4 + 0], &a);
+            if (rc == ARCTE_OK) rc = localise(c, dev_seg_count[p], S * sizeof(int32_t), stage[(size_t)p * 4 + 1], &b);
+            if (rc == ARCTE_OK) rc = localise(c, dev_seg_offset[p], S * sizeof(int64_t), stage[(size_t)p * 4 + 2], &d);
+            if (rc == ARCTE_OK) rc = localise(c, dev_members[p], M * sizeof(int32_t), stage[(size_t)p * 4 + 3], &e);
+            parts.push_back(SegPart{part_n_segments[p], (const int32_t *)a, (const int32_t *)b,
+                                    (const int64_t *)d, (const int32_t *)e});
+        }
+    }
+    if (rc == ARCTE_OK) rc = assemble_parts(c, (int)parts.size(), parts.data());
+    for (DevBuf &b : stage) dev_free(b);
+    if (rc != ARCTE_OK) return rc;
+    if (nnz_out) *nnz_out = c->out_nnz;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data)
+{
+    CHECK_CTX(c);
+    if (!c->have_features) { set_error("get_features: call assemble first"); return ARCTE_E_ARG; }
+    if (host_indptr)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->out_indptr.p, sizeof(int64_t) * (size_t)(c->n + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (host_indices && c->out_nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indices, c->out_indices.p, sizeof(int32_t) * (size_t)c->out_nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (host_data && c->out_nnz > 0)
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_data, c->out_data.p, sizeof(double) * (size_t)c->out_nnz, cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_timer_start(arcte_cuda_ctx *c)
+{
+    CHECK_CTX(c);
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ARCTE_CUDA_TRY(cudaEventRecord(c->tm0, c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_timer_stop(arcte_cuda_ctx *c, double *elapsed_ms)
+{
+    CHECK_CTX(c);
+    ARCTE_CUDA_TRY(cudaEventRecord(c->tm1, c->stream));
+    ARCTE_CUDA_TRY(cudaEventSynchronize(c->tm1));
+    float ms = 0.f;
+    ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, c->tm0, c->tm1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_flush_l2(arcte_cuda_ctx *c)
+{
+    CHECK_CTX(c);
+    const size_t bytes = size_t(512) << 20;
+    ARCTE_TRY(dev_reserve(c->l2_flush, bytes));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->l2_flush.p, 0x5a, bytes, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_stats(arcte_cuda_ctx *c, arcte_cuda_stats *out)
+{
+    if (!c || !out) { set_error("get_stats: null argument"); return ARCTE_E_ARG; }
+    *out = c->stats;
+    return ARCTE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// common.cuh -- context layout, error handling and small device helpers shared by
+// the translation units of libarcte_cuda.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/arcte_cuda.h"
+
+namespace arcte {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+void set_error(const std::string &msg);
+
+#define ARCTE_CUDA_TRY(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::arcte::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +    \
+                               __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
+            return ARCTE_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ARCTE_TRY(expr)                  \
+    do {                                 \
+        int _rc = (expr);                \
+        if (_rc != ARCTE_OK) return _rc; \
+    } while (0)
+
+// A device allocation that remembers its size so buffers can be grown lazily.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+int dev_reserve(DevBuf &b, size_t bytes);  // grow-only, contents not preserved
+void dev_free(DevBuf &b);
+
+// Per-seed walk state of one warp ("slot"): interleaved {s, r} pairs over all n
+// nodes (always all-zero between seeds), the touched list and the FIFO ring.
+struct SlotPool {
+    DevBuf sr;       // double2 [n_slots][n]
+    DevBuf touched;  // int32   [n_slots][n]
+    DevBuf queue;    // int32   [n_slots][queue_cap]
+    int64_t n_slots = 0;      // state/touched rows allocated
+    int64_t queue_slots = 0;  // FIFO rings allocated (== n_slots except after a retry grew the rings)
+    int64_t queue_cap = 0;
+    int64_t n = 0;
+};
+
+// Device-side counters of the fused push kernel (one int64 each, atomically added).
+enum PushCounter {
+    PC_PUSHES = 0, PC_EDGES, PC_ENQUEUES, PC_MAXQ, PC_SUPPORT, PC_TOUCHED, PC_SEEDDEG, PC_MEMBERS,
+    PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR, PC_COUNT
+};
+
+}  // namespace arcte
+
+struct arcte_cuda_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // caller-visible step timer
+    arcte::DevBuf l2_flush;
+
+    // tuning
+    int warps_per_sm = 0;      // 0 = default
+    int64_t queue_cap_cfg = 0; // 0 = default
+    int mem_percent = 0;       // 0 = default
+    int64_t member_cap_cfg = 0; // 0 = default
+
+    // graph (adjacency + transition), all resident
+    int64_t n = 0, nnz = 0;
+    arcte::DevBuf indptr;   // int64 [n+1]
+    arcte::DevBuf indices;  // int32 [nnz]
+    arcte::DevBuf adj;      // double [nnz]  adjacency weights
+    arcte::DevBuf w;        // double [nnz]  transition probabilities
+    arcte::DevBuf d_out;    // double [n]
+    arcte::DevBuf d_in;     // double [n]
+    arcte::DevBuf colcnt;   // int32 [n]  binarised column counts
+    bool have_graph = false, have_transition = false;
+
+    // seeds
+    arcte::DevBuf seeds;    // int32 [n]  count-descending, first n_seeds valid
+    int64_t n_seeds = 0;
+
+    // extraction results (segments of this context's shard)
+    arcte::DevBuf work_seed;   // int32 [S]  seed node per segment
+    arcte::DevBuf work_eps;    // double [S]
+    arcte::DevBuf seg_count;   // int32 [S]
+    arcte::DevBuf seg_offset;  // int64 [S]
+    arcte::DevBuf members;     // int32 [member_cap]
+    arcte::DevBuf retry_list;  // int32 [S]  positions whose FIFO overflowed
+    int64_t n_segments = 0, n_members = 0, member_cap = 0;
+    bool have_segments = false;
+
+    arcte::SlotPool slots;
+    arcte::DevBuf counters;  // int64 [PC_COUNT]
+
+    // assembly output
+    arcte::DevBuf out_indptr;   // int64 [n+1]
+    arcte::DevBuf out_indices;  // int32 [nnz_out]
+    arcte::DevBuf out_data;     // double [nnz_out]
+    int64_t out_nnz = 0;
+    bool have_features = false;
+
+    // scratch shared by primitives
+    arcte::DevBuf scratch[16];
+
+    arcte_cuda_stats stats{};
+};
+
+namespace arcte {
+
+// ---- device helpers -----------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// numpy's DOUBLE_pairwise_sum over n values produced by `at(i)`: identical tree and
+// therefore identical rounding to np.add.reduce on a contiguous float64 array
+// (blocks of <=128 elements with 8 strided accumulators, halves split on multiples of 8).
+template <typename F> __device__ double pairwise_sum(F at, int64_t off, int64_t n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, at(off + i));
+        return res;
+    } else if (n <= 128) {
+        double r0 = at(off + 0), r1 = at(off + 1), r2 = at(off + 2), r3 = at(off + 3);
+        double r4 = at(off + 4), r5 = at(off + 5), r6 = at(off + 6), r7 = at(off + 7);
+        int64_t i;
+        const int64_t lim = n - (n % 8);
+        for (i = 8; i < lim; i += 8) {
+            r0 = __dadd_rn(r0, at(off + i + 0));
+            r1 = __dadd_rn(r1, at(off + i + 1));
+            r2 = __dadd_rn(r2, at(off + i + 2));
+            r3 = __dadd_rn(r3, at(off + i + 3));
+            r4 = __dadd_rn(r4, at(off + i + 4));
+            r5 = __dadd_rn(r5, at(off + i + 5));
+            r6 = __dadd_rn(r6, at(off + i + 6));
+            r7 = __dadd_rn(r7, at(off + i + 7));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                               __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+        for (; i < n; ++i) res = __dadd_rn(res, at(off + i));
+        return res;
+    } else {
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        const double a = pairwise_sum(at, off, n2);
+        const double b = pairwise_sum(at, off + n2, n - n2);
+        return __dadd_rn(a, b);
+    }
+}
+
+}  // namespace arcte

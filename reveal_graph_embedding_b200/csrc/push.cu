@@ -1,0 +1,748 @@
+// push.cu -- K3 + K4: the batched epsilon-push engine fused with the per-seed threshold
+// and the stream compaction of community members.
+//
+// Reference being replaced (paths relative to /root/reference/reveal_graph_embedding/):
+//   drivers   fast_approximate_cumulative_pagerank_difference   eps_randomwalk/similarity.py:149-222
+//             fast_approximate_personalized_pagerank            eps_randomwalk/similarity.py:11-63
+//             lazy_approximate_personalized_pagerank            eps_randomwalk/similarity.py:66-146
+//   rules     cumulative_pagerank_difference_limit_push         eps_randomwalk/push.py:41-64
+//             pagerank_limit_push / pagerank_lazy_push          eps_randomwalk/push.py:4-38
+//   worker    arcte_worker (threshold + membership)             embedding/arcte/arcte.py:328-376
+//             guarded variants                                  embedding/arcte/arcte.py:121-152, 233-264
+//
+// Execution model.  One warp owns one seed at a time ("slot"): a dense, always-zero-
+// between-seeds array of interleaved {s, r} pairs over all n nodes in HBM, a list of the
+// nodes it touched (sparse reset instead of the reference's O(n) clears) and a FIFO
+// ring.  The warp replays the reference's queue discipline EXACTLY -- same pop order,
+// same CSR-order enqueue of the neighbours that pass r/d_in >= eps, duplicates kept --
+// with the 32 lanes spread over the pushed node's neighbour list.  Every fp64 operation
+// is a single IEEE rounding (__dmul_rn/__dadd_rn/__ddiv_rn, no FMA contraction), so s and
+// r are bit-identical to numpy's and the thresholded support is identical, not merely
+// within the push error bound.  Thousands of slots are in flight per GPU; seeds are
+// pulled from a degree-descending work list through one atomic counter.
+#include "common.cuh"
+
+namespace arcte {
+
+struct PushParams {
+    int64_t n;
+    const int64_t *indptr;
+    const int32_t *indices;
+    const double *w;
+    const double *d_in;
+    // work list
+    const int32_t *work_seed;  // [n_work_total] seed node per position
+    const double *work_eps;    // [n_work_total]
+    const int32_t *work_ids;   // positions to run (retry pass) or nullptr = 0..n_work-1
+    int64_t n_work;
+    int retry_pass;
+    // slots
+    double2 *sr;
+    int32_t *touched;
+    int32_t *queue;
+    int64_t queue_cap;  // power of two
+    int64_t n_slots;
+    // outputs
+    int32_t *seg_count;
+    int64_t *seg_offset;
+    int32_t *members;
+    int64_t member_cap;
+    int32_t *retry_list;
+    unsigned long long *counters;
+    // rule constants, computed on the host exactly as Python evaluates them
+    double rho;            // rho
+    double one_minus_rho;  // (1-rho)
+    double lazy_b;         // (1-rho)*(1-lazy)
+    double lazy_c;         // (1-rho)*lazy
+    int debug_keep;        // operator seam: stop after the walk, leave s/r in slot 0
+};
+
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ int64_t warp_sum(int64_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Walk state of the warp for the current seed.
+struct Walk {
+    int64_t head, tail;  // FIFO
+    int nt;              // touched count
+    int64_t pushes, edges, enq, maxq;
+};
+
+// One push of node u whose state pair su was just read, then (scan) the enqueue scan.
+// Returns false when the FIFO ring would overflow (nothing is lost: caller aborts the seed).
+template <int RULE>
+__device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restrict__ sr,
+                                          int32_t *__restrict__ touched, int32_t *__restrict__ queue,
+                                          Walk &wk, int u, double2 su, double eps, bool scan, int lane,
+                                          unsigned lt)
+{
+    double c;
+    if (RULE == ARCTE_RULE_ABSORBING) {
+        c = __dmul_rn(P.one_minus_rho, su.y);            // push.py:57
+        if (lane == 0) sr[u] = make_double2(su.x, 0.0);  // push.py:60
+    } else if (RULE == ARCTE_RULE_PAGERANK) {
+        const double a = __dmul_rn(P.rho, su.y);          // push.py:9
+        c = __dmul_rn(P.one_minus_rho, su.y);             // push.py:10
+        if (lane == 0) sr[u] = make_double2(__dadd_rn(su.x, a), 0.0);  // push.py:13-14
+    } else {
+        const double a = __dmul_rn(P.rho, su.y);          // push.py:29
+        c = __dmul_rn(P.lazy_b, su.y);                    // push.py:30
+        const double keep = __dmul_rn(P.lazy_c, su.y);    // push.py:31
+        if (lane == 0) sr[u] = make_double2(__dadd_rn(su.x, a), keep);  // push.py:34-35
+    }
+    __syncwarp();
+    const int64_t b = P.indptr[u], e = P.indptr[u + 1];
+    wk.pushes += 1;
+    wk.edges += e - b;
+    const int64_t qmask = P.queue_cap - 1;
+    for (int64_t j0 = b; j0 < e; j0 += 32) {
+        const int64_t j = j0 + lane;
+        int v = 0;
+        bool is_new = false, enq = false;
+        if (j < e) {
+            v = P.indices[j];
+            const double p = __dmul_rn(c, P.w[j]);
+            const double2 o = sr[v];
+            double2 nw;
+            if (RULE == ARCTE_RULE_ABSORBING) {
+                nw.x = __dadd_rn(o.x, p);  // push.py:63
+                nw.y = __dadd_rn(o.y, p);  // push.py:64
+            } else {
+                nw.x = o.x;
+                nw.y = __dadd_rn(o.y, p);  // push.py:17 / :38
+            }
+            sr[v] = nw;
+            is_new = (o.x == 0.0 && o.y == 0.0) && (nw.x != 0.0 || nw.y != 0.0);
+            if (scan) enq = __ddiv_rn(nw.y, P.d_in[v]) >= eps;  // similarity.py:194 / :214
+        }
+        const unsigned m_new = __ballot_sync(kFull, is_new);
+        if (is_new) touched[wk.nt + __popc(m_new & lt)] = v;
+        wk.nt += __popc(m_new);
+        if (scan) {
+            const unsigned m_enq = __ballot_sync(kFull, enq);
+            const int cnt = __popc(m_enq);
+            if (cnt) {
+                if (wk.tail - wk.head + cnt > P.queue_cap) return false;
+                if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = v;  // CSR order
+                wk.tail += cnt;
+                wk.enq += cnt;
+            }
+        }
+    }
+    if (wk.tail - wk.head > wk.maxq) wk.maxq = wk.tail - wk.head;
+    __syncwarp();
+    return true;
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(256)
+k_push_threshold(const PushParams P)
+{
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= P.n_slots) return;
+    double2 *__restrict__ sr = P.sr + slot * P.n;
+    int32_t *__restrict__ touched = P.touched + slot * P.n;
+    int32_t *__restrict__ queue = P.queue + slot * P.queue_cap;
+    const int64_t qmask = P.queue_cap - 1;
+
+    int64_t a_pushes = 0, a_edges = 0, a_enq = 0, a_maxq = 0, a_support = 0, a_touched = 0;
+    int64_t a_seeddeg = 0, a_members = 0, a_emitted = 0;
+
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&P.counters[PC_WORK_CURSOR], 1ull);
+        k = __shfl_sync(kFull, k, 0);
+        if ((int64_t)k >= P.n_work) break;
+        const int64_t pos = P.work_ids ? (int64_t)P.work_ids[k] : (int64_t)k;
+        const int seed = P.work_seed[pos];
+        const double eps = P.work_eps[pos];
+
+        Walk wk;
+        wk.head = wk.tail = 0;
+        wk.nt = 0;
+        wk.pushes = wk.edges = wk.enq = wk.maxq = 0;
+
+        // similarity.py:176-177 (absorbing) / :26, :84 (pagerank variants)
+        double2 su = make_double2(RULE == ARCTE_RULE_ABSORBING ? 1.0 : 0.0, 1.0);
+        if (lane == 0) {
+            sr[seed] = su;
+            touched[0] = seed;
+        }
+        wk.nt = 1;
+        __syncwarp();
+
+        // "Do one push for free" + first enqueue scan (similarity.py:183-196)
+        bool ok = push_node<RULE>(P, sr, touched, queue, wk, seed, su, eps, true, lane, lt);
+        if (ok && RULE == ARCTE_RULE_LAZY) {
+            // similarity.py:106-114: repeated self pushes of the seed, no enqueue scan
+            const double du = P.d_in[seed];
+            su = sr[seed];
+            while (__ddiv_rn(su.y, du) >= eps) {
+                push_node<RULE>(P, sr, touched, queue, wk, seed, su, eps, false, lane, lt);
+                su = sr[seed];
+            }
+        }
+        // similarity.py:199-216
+        while (ok && wk.head < wk.tail) {
+            const int u = queue[wk.head & qmask];
+            wk.head += 1;
+            const double du = P.d_in[u];
+            su = sr[u];
+            if (__ddiv_rn(su.y, du) >= eps) {  // similarity.py:204
+                ok = push_node<RULE>(P, sr, touched, queue, wk, u, su, eps, true, lane, lt);
+                if (!ok) break;
+            }
+            if (RULE == ARCTE_RULE_LAZY) {  // similarity.py:134-142
+                su = sr[u];
+                while (__ddiv_rn(su.y, du) >= eps) {
+                    push_node<RULE>(P, sr, touched, queue, wk, u, su, eps, false, lane, lt);
+                    su = sr[u];
+                }
+            }
+        }
+
+        if (P.debug_keep) {
+            if (lane == 0) {
+                P.counters[PC_PUSHES] = (unsigned long long)wk.pushes;
+                P.counters[PC_TOUCHED] = (unsigned long long)wk.nt;
+                P.counters[PC_OVERFLOW_SEEDS] = ok ? 0ull : 1ull;
+            }
+            return;
+        }
+
+        if (!ok) {
+            // FIFO ring too small: undo and hand the seed to the retry pass
+            for (int i = lane; i < wk.nt; i += 32) sr[touched[i]] = make_double2(0.0, 0.0);
+            if (lane == 0) {
+                const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
+                P.retry_list[r] = (int32_t)pos;
+                atomicAdd(&P.counters[PC_QOVERFLOW], 1ull);
+                P.seg_count[pos] = -1;
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // ---------------- K4: threshold + membership (arcte.py:352-376) ----------------
+        const int64_t b = P.indptr[seed], e = P.indptr[seed + 1];
+        const int64_t base_size = (e - b) + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
+        bool emit = true;
+        if (RULE != ARCTE_RULE_ABSORBING) {
+            // arcte.py:129-133 / :241-245: intersect1d(base, support).size >= base.size
+            int64_t inside = 0;
+            for (int64_t j = b + lane; j < e; j += 32) {
+                const int v = P.indices[j];
+                inside += (v != seed && sr[v].x != 0.0);
+            }
+            inside = warp_sum(inside) + (sr[seed].x != 0.0 ? 1 : 0);
+            emit = inside >= base_size;
+        }
+        int64_t m = 0, support = 0;
+        double tau = 0.0;
+        if (emit) {
+            double q = INFINITY;
+            for (int64_t j = b + lane; j < e; j += 32) {
+                const int v = P.indices[j];
+                q = fmin(q, __ddiv_rn(sr[v].x, P.d_in[v]));  // arcte.py:355-356
+            }
+            q = fmin(q, __ddiv_rn(sr[seed].x, P.d_in[seed]));
+            tau = warp_min(q);  // arcte.py:359-360
+        }
+        // count of support entries with q >= tau (arcte.py:363-367; searchsorted 'left')
+        for (int i0 = 0; i0 < wk.nt; i0 += 32) {
+            const int i = i0 + lane;
+            bool in_sup = false, pass = false;
+            if (i < wk.nt) {
+                const int x = touched[i];
+                const double sx = sr[x].x;
+                in_sup = sx != 0.0;
+                pass = emit && in_sup && (__ddiv_rn(sx, P.d_in[x]) >= tau);
+            }
+            support += __popc(__ballot_sync(kFull, in_sup));
+            m += __popc(__ballot_sync(kFull, pass));
+        }
+        emit = emit && (m > base_size);  // arcte.py:370
+        int64_t off = 0;
+        bool write = false;
+        if (emit) {
+            if (P.retry_pass && P.seg_count[pos] > 0) {
+                off = P.seg_offset[pos];  // offset was assigned in the pass that overflowed
+            } else {
+                unsigned long long o = 0;
+                if (lane == 0) o = atomicAdd(&P.counters[PC_MEMBER_CURSOR], (unsigned long long)m);
+                off = (int64_t)__shfl_sync(kFull, o, 0);
+            }
+            write = off + m <= P.member_cap;
+            if (lane == 0) {
+                P.seg_count[pos] = (int32_t)m;
+                P.seg_offset[pos] = off;
+                if (!write) {
+                    const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
+                    P.retry_list[r] = (int32_t)pos;
+                }
+            }
+        } else if (lane == 0) {
+            P.seg_count[pos] = 0;
+            P.seg_offset[pos] = 0;
+        }
+        // second sweep: compact the members (arcte.py:372-376) and reset the slot
+        int64_t written = 0;
+        for (int i0 = 0; i0 < wk.nt; i0 += 32) {
+            const int i = i0 + lane;
+            int x = 0;
+            bool pass = false;
+            if (i < wk.nt) {
+                x = touched[i];
+                if (write) {
+                    const double sx = sr[x].x;
+                    pass = sx != 0.0 && (__ddiv_rn(sx, P.d_in[x]) >= tau);
+                }
+                sr[x] = make_double2(0.0, 0.0);  // sparse form of s[:]=0; r[:]=0 (arcte.py:337-338)
+            }
+            if (write) {
+                const unsigned mp = __ballot_sync(kFull, pass);
+                if (pass) P.members[off + written + __popc(mp & lt)] = x;
+                written += __popc(mp);
+            }
+        }
+        __syncwarp();
+
+        if (!emit || write) {  // a seed whose members did not fit is re-run and counted then
+            a_pushes += wk.pushes; a_edges += wk.edges; a_enq += wk.enq;
+            if (wk.maxq > a_maxq) a_maxq = wk.maxq;
+            a_support += support; a_touched += wk.nt; a_seeddeg += e - b;
+            if (emit) { a_members += m; a_emitted += 1; }
+        }
+    }
+
+    if (lane == 0 && !P.debug_keep) {
+        atomicAdd(&P.counters[PC_PUSHES], (unsigned long long)a_pushes);
+        atomicAdd(&P.counters[PC_EDGES], (unsigned long long)a_edges);
+        atomicAdd(&P.counters[PC_ENQUEUES], (unsigned long long)a_enq);
+        atomicMax(&P.counters[PC_MAXQ], (unsigned long long)a_maxq);
+        atomicAdd(&P.counters[PC_SUPPORT], (unsigned long long)a_support);
+        atomicAdd(&P.counters[PC_TOUCHED], (unsigned long long)a_touched);
+        atomicAdd(&P.counters[PC_SEEDDEG], (unsigned long long)a_seeddeg);
+        atomicAdd(&P.counters[PC_MEMBERS], (unsigned long long)a_members);
+        atomicAdd(&P.counters[PC_EMITTED], (unsigned long long)a_emitted);
+    }
+}
+
+// ---- small helper kernels ---------------------------------------------------------------
+__global__ void k_build_work(int64_t n_work, int shard_rank, int shard_count,
+                             const int32_t *__restrict__ seeds, int32_t *__restrict__ work_seed)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_work) work_seed[i] = seeds[shard_rank + i * shard_count];  // arcte.py:19-23
+}
+
+__global__ void k_gather_eps(int64_t n_work, int shard_rank, int shard_count,
+                             const double *__restrict__ eps_global, double *__restrict__ work_eps)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_work) work_eps[i] = eps_global[shard_rank + i * shard_count];
+}
+
+__global__ void k_split_and_reset(int64_t n, int64_t n_touched, double2 *__restrict__ sr,
+                                  const int32_t *__restrict__ touched, double *__restrict__ s_out,
+                                  double *__restrict__ r_out, int phase)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 0) {
+        if (i < n) {
+            const double2 v = sr[i];
+            s_out[i] = v.x;
+            r_out[i] = v.y;
+        }
+    } else if (i < n_touched) {
+        sr[touched[i]] = make_double2(0.0, 0.0);
+    }
+}
+
+static inline unsigned grid_for(int64_t items, int block) { return (unsigned)((items + block - 1) / block); }
+
+int compute_eps_effective(arcte_cuda_ctx *c, double epsilon, const int32_t *dev_seeds,
+                          int64_t n_seeds, double *dev_eps_out);
+
+// Allocate (or re-shape) the slot pool.  States are zeroed once here and every seed
+// leaves its slot all-zero again, so the pool is reused across extractions as is.
+static int ensure_slots(arcte_cuda_ctx *c, int64_t want_slots, int64_t queue_cap)
+{
+    SlotPool &sp = c->slots;
+    const bool same_state = (sp.n == c->n && sp.n_slots >= want_slots);
+    if (!same_state) {
+        dev_free(sp.sr);
+        dev_free(sp.touched);
+        dev_free(sp.queue);
+        sp.n_slots = sp.queue_slots = 0;
+        ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)want_slots * (size_t)c->n));
+        ARCTE_TRY(dev_reserve(sp.touched, sizeof(int32_t) * (size_t)want_slots * (size_t)c->n));
+        ARCTE_CUDA_TRY(cudaMemsetAsync(sp.sr.p, 0, sizeof(double2) * (size_t)want_slots * (size_t)c->n,
+                                       c->stream));
+        sp.n = c->n;
+        sp.n_slots = want_slots;
+    }
+    if (sp.queue_cap != queue_cap || sp.queue_slots < want_slots) {
+        dev_free(sp.queue);
+        ARCTE_TRY(dev_reserve(sp.queue, sizeof(int32_t) * (size_t)sp.n_slots * (size_t)queue_cap));
+        sp.queue_cap = queue_cap;
+        sp.queue_slots = sp.n_slots;
+    }
+    return ARCTE_OK;
+}
+
+static int64_t pow2_at_least(int64_t v)
+{
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static void fill_rule_constants(PushParams &P, double rho)
+{
+    const double lazy = 0.5;  // similarity.py:75 default, the only value the reference uses
+    P.rho = rho;
+    P.one_minus_rho = 1.0 - rho;
+    P.lazy_b = (1.0 - rho) * (1.0 - lazy);
+    P.lazy_c = (1.0 - rho) * lazy;
+}
+
+static int launch_push(arcte_cuda_ctx *c, int rule, const PushParams &P)
+{
+    const unsigned grid = grid_for(P.n_slots * 32, 256);
+    switch (rule) {
+    case ARCTE_RULE_ABSORBING: k_push_threshold<ARCTE_RULE_ABSORBING><<<grid, 256, 0, c->stream>>>(P); break;
+    case ARCTE_RULE_PAGERANK: k_push_threshold<ARCTE_RULE_PAGERANK><<<grid, 256, 0, c->stream>>>(P); break;
+    case ARCTE_RULE_LAZY: k_push_threshold<ARCTE_RULE_LAZY><<<grid, 256, 0, c->stream>>>(P); break;
+    default: set_error("unknown push rule"); return ARCTE_E_ARG;
+    }
+    ++c->stats.launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    return ARCTE_OK;
+}
+
+// Slot-pool geometry for this graph: how many walks can be in flight.
+static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap)
+{
+    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : 32;
+    int64_t want = (int64_t)c->sm_count * wps;
+    want = ((want + 7) / 8) * 8;
+    int64_t qcap = c->queue_cap_cfg > 0 ? c->queue_cap_cfg : (c->n < 65536 ? c->n : 65536);
+    if (qcap < 64) qcap = 64;
+    qcap = pow2_at_least(qcap);
+    if (want > ((n_work + 7) / 8) * 8) want = ((n_work + 7) / 8) * 8;
+    if (want < 8) want = 8;
+    // keep whatever is already allocated if it is big enough (avoids re-zeroing)
+    if (c->slots.n == c->n && c->slots.n_slots >= want && c->slots.queue_slots >= want &&
+        c->slots.queue_cap == qcap) {
+        *n_slots = want;
+        *queue_cap = qcap;
+        return ARCTE_OK;
+    }
+    size_t free_b = 0, total_b = 0;
+    ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes;
+    const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
+    const double budget = (double)free_b * pct / 100.0;
+    const double per_slot = 16.0 * c->n + 4.0 * c->n + 4.0 * qcap;
+    int64_t fit = (int64_t)(budget / per_slot);
+    fit = (fit / 8) * 8;
+    if (fit < 8) {
+        set_error("not enough device memory for 8 walk states of this graph");
+        return ARCTE_E_NOMEM;
+    }
+    if (want > fit) want = fit;
+    *n_slots = want;
+    *queue_cap = qcap;
+    return ARCTE_OK;
+}
+
+int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int shard_rank,
+                  int shard_count, const double *host_eps_override)
+{
+    if (!c->have_transition) { set_error("extract: no transition matrix (call set_graph)"); return ARCTE_E_ARG; }
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) {
+        set_error("extract: bad shard");
+        return ARCTE_E_ARG;
+    }
+    cudaStream_t st = c->stream;
+    const int64_t S = c->n_seeds > shard_rank ? (c->n_seeds - shard_rank + shard_count - 1) / shard_count : 0;
+    c->n_segments = S;
+    c->n_members = 0;
+    c->have_segments = false;
+    c->have_features = false;
+    arcte_cuda_stats &stt = c->stats;
+    stt.n_seeds_shard = S;
+    stt.pushes = stt.edge_touches = stt.enqueues = stt.max_queue = stt.support = stt.touched = 0;
+    stt.seed_degree = stt.members = stt.emitted = stt.retries = 0;
+    stt.ms_push = 0.0;
+    stt.alg_bytes_push = 0.0;
+
+    const size_t S1 = (size_t)(S > 0 ? S : 1);
+    ARCTE_TRY(dev_reserve(c->work_seed, sizeof(int32_t) * S1));
+    ARCTE_TRY(dev_reserve(c->work_eps, sizeof(double) * S1));
+    ARCTE_TRY(dev_reserve(c->seg_count, sizeof(int32_t) * S1));
+    ARCTE_TRY(dev_reserve(c->seg_offset, sizeof(int64_t) * S1));
+    ARCTE_TRY(dev_reserve(c->retry_list, sizeof(int32_t) * S1));
+    ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
+    if (S == 0) {
+        c->have_segments = true;
+        return ARCTE_OK;
+    }
+
+    // ---- K2b: work list + epsilon-effective ----
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
+    k_build_work<<<grid_for(S, 256), 256, 0, st>>>(S, shard_rank, shard_count, c->seeds.as<int32_t>(),
+                                                   c->work_seed.as<int32_t>());
+    ++stt.launches;
+    if (host_eps_override) {
+        ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * (size_t)c->n_seeds));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[2].p, host_eps_override,
+                                       sizeof(double) * (size_t)c->n_seeds, cudaMemcpyHostToDevice, st));
+        k_gather_eps<<<grid_for(S, 256), 256, 0, st>>>(S, shard_rank, shard_count,
+                                                       c->scratch[2].as<double>(), c->work_eps.as<double>());
+        ++stt.launches;
+    } else {
+        ARCTE_TRY(compute_eps_effective(c, epsilon, c->work_seed.as<int32_t>(), S, c->work_eps.as<double>()));
+    }
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
+
+    // ---- slot pool + member buffer ----
+    int64_t n_slots = 0, qcap = 0;
+    ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap));
+    ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    if (c->member_cap == 0) {
+        // default: a tenth of what is free now, never more than the n_seeds x n worst case
+        size_t free_b = 0, total_b = 0;
+        ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        int64_t cap = c->member_cap_cfg;
+        if (cap <= 0) {
+            cap = (int64_t)(free_b / 10 / sizeof(int32_t));
+            const double worst = (double)S * (double)c->n;
+            if ((double)cap > worst) cap = (int64_t)worst;
+            if (cap < (1 << 20)) cap = 1 << 20;
+        }
+        ARCTE_TRY(dev_reserve(c->members, sizeof(int32_t) * (size_t)cap));
+        c->member_cap = cap;
+    }
+
+    PushParams P{};
+    P.n = c->n;
+    P.indptr = c->indptr.as<int64_t>();
+    P.indices = c->indices.as<int32_t>();
+    P.w = c->w.as<double>();
+    P.d_in = c->d_in.as<double>();
+    P.work_seed = c->work_seed.as<int32_t>();
+    P.work_eps = c->work_eps.as<double>();
+    P.work_ids = nullptr;
+    P.n_work = S;
+    P.retry_pass = 0;
+    P.sr = c->slots.sr.as<double2>();
+    P.touched = c->slots.touched.as<int32_t>();
+    P.queue = c->slots.queue.as<int32_t>();
+    P.queue_cap = c->slots.queue_cap;
+    P.n_slots = n_slots;
+    P.seg_count = c->seg_count.as<int32_t>();
+    P.seg_offset = c->seg_offset.as<int64_t>();
+    P.members = c->members.as<int32_t>();
+    P.member_cap = c->member_cap;
+    P.retry_list = c->retry_list.as<int32_t>();
+    P.counters = c->counters.as<unsigned long long>();
+    P.debug_keep = 0;
+    fill_rule_constants(P, rho);
+
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->seg_count.p, 0, sizeof(int32_t) * (size_t)S, st));
+    cudaEvent_t p0, p1;
+    ARCTE_CUDA_TRY(cudaEventCreate(&p0));
+    ARCTE_CUDA_TRY(cudaEventCreate(&p1));
+    ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
+    ARCTE_TRY(launch_push(c, rule, P));
+    ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
+
+    int64_t hc[PC_COUNT];
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    stt.ms_seeds += ms;
+    ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, p0, p1));
+    stt.ms_push = ms;
+    stt.n_slots = n_slots;
+
+    // ---- retry passes: seeds whose FIFO ring or member range did not fit ----
+    int rounds = 0;
+    while (hc[PC_OVERFLOW_SEEDS] > 0) {
+        const int64_t n_retry = hc[PC_OVERFLOW_SEEDS];
+        stt.retries += n_retry;
+        if (++rounds > 12) { set_error("extract: retry passes did not converge"); return ARCTE_E_OVERFLOW; }
+        // members: grow to the exact demand seen so far (+ headroom for the seeds still to run)
+        if (hc[PC_MEMBER_CURSOR] > c->member_cap || hc[PC_QOVERFLOW] > 0) {
+            int64_t new_cap = hc[PC_MEMBER_CURSOR] + (hc[PC_QOVERFLOW] > 0 ? c->member_cap : 0);
+            if (new_cap > c->member_cap) {
+                DevBuf nb;
+                ARCTE_TRY(dev_reserve(nb, sizeof(int32_t) * (size_t)new_cap));
+                ARCTE_CUDA_TRY(cudaMemcpyAsync(nb.p, c->members.p, sizeof(int32_t) * (size_t)c->member_cap,
+                                               cudaMemcpyDeviceToDevice, st));
+                ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+                dev_free(c->members);
+                c->members = nb;
+                c->member_cap = new_cap;
+            }
+        }
+        int64_t r_slots = ((n_retry + 7) / 8) * 8;
+        if (r_slots > c->slots.queue_slots) r_slots = c->slots.queue_slots;
+        int64_t r_qcap = c->slots.queue_cap;
+        if (hc[PC_QOVERFLOW] > 0) {
+            // a bigger ring for fewer walks: same bytes first, then grow
+            r_qcap = c->slots.queue_cap * 8;
+            size_t free_b = 0, total_b = 0;
+            ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            free_b += c->slots.queue.bytes;
+            while (r_slots > 8 && (double)r_slots * r_qcap * 4.0 > 0.8 * (double)free_b) r_slots -= 8;
+            if ((double)r_slots * r_qcap * 4.0 > 0.8 * (double)free_b) {
+                set_error("extract: FIFO ring cannot be grown further (out of device memory)");
+                return ARCTE_E_OVERFLOW;
+            }
+            dev_free(c->slots.queue);
+            ARCTE_TRY(dev_reserve(c->slots.queue, sizeof(int32_t) * (size_t)r_slots * (size_t)r_qcap));
+            c->slots.queue_cap = r_qcap;
+            c->slots.queue_slots = r_slots;  // fewer, larger rings until the next plan_slots
+        }
+        // retry list -> scratch (the kernel appends to retry_list again)
+        ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * (size_t)n_retry));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[0].p, c->retry_list.p, sizeof(int32_t) * (size_t)n_retry,
+                                       cudaMemcpyDeviceToDevice, st));
+        // keep accumulated counters except the cursors that restart
+        int64_t zero = 0;
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->counters.as<int64_t>() + PC_WORK_CURSOR, &zero, sizeof(zero),
+                                       cudaMemcpyHostToDevice, st));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->counters.as<int64_t>() + PC_OVERFLOW_SEEDS, &zero, sizeof(zero),
+                                       cudaMemcpyHostToDevice, st));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->counters.as<int64_t>() + PC_QOVERFLOW, &zero, sizeof(zero),
+                                       cudaMemcpyHostToDevice, st));
+        P.work_ids = c->scratch[0].as<int32_t>();
+        P.n_work = n_retry;
+        P.retry_pass = 1;
+        P.queue = c->slots.queue.as<int32_t>();
+        P.queue_cap = c->slots.queue_cap;
+        P.n_slots = r_slots;
+        P.members = c->members.as<int32_t>();
+        P.member_cap = c->member_cap;
+        ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
+        ARCTE_TRY(launch_push(c, rule, P));
+        ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+        ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, p0, p1));
+        stt.ms_push += ms;
+    }
+    cudaEventDestroy(p0);
+    cudaEventDestroy(p1);
+
+    stt.pushes = hc[PC_PUSHES];
+    stt.edge_touches = hc[PC_EDGES];
+    stt.enqueues = hc[PC_ENQUEUES];
+    stt.max_queue = hc[PC_MAXQ];
+    stt.support = hc[PC_SUPPORT];
+    stt.touched = hc[PC_TOUCHED];
+    stt.seed_degree = hc[PC_SEEDDEG];
+    stt.members = hc[PC_MEMBERS];
+    stt.emitted = hc[PC_EMITTED];
+    // sum_pushes(24 + 52 deg(u)) + sum_seeds(32 |supp| + 12 deg(seed) + 12 |comm|)
+    stt.alg_bytes_push = 24.0 * stt.pushes + 52.0 * stt.edge_touches + 32.0 * stt.support +
+                         12.0 * stt.seed_degree + 12.0 * stt.members;
+    c->n_members = hc[PC_MEMBER_CURSOR];
+    c->have_segments = true;
+    return ARCTE_OK;
+}
+
+// Operator seam: one seed, dense s and r back to the host.
+int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double eps_eff, double *host_s,
+                double *host_r, int64_t *n_push)
+{
+    if (!c->have_transition) { set_error("push: no transition matrix (call set_graph)"); return ARCTE_E_ARG; }
+    if (seed < 0 || seed >= c->n) { set_error("push: seed out of range"); return ARCTE_E_ARG; }
+    cudaStream_t st = c->stream;
+    int64_t n_slots = 0, qcap = 0;
+    ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
+    ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
+    ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * 4));
+    ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * 4));
+    ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(double) * 2 * (size_t)c->n));
+    const int32_t seed32 = (int32_t)seed;
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[0].p, &seed32, sizeof(seed32), cudaMemcpyHostToDevice, st));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[2].p, &eps_eff, sizeof(eps_eff), cudaMemcpyHostToDevice, st));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
+
+    int64_t cap = c->slots.queue_cap;
+    for (int attempt = 0;; ++attempt) {
+        PushParams P{};
+        P.n = c->n;
+        P.indptr = c->indptr.as<int64_t>();
+        P.indices = c->indices.as<int32_t>();
+        P.w = c->w.as<double>();
+        P.d_in = c->d_in.as<double>();
+        P.work_seed = c->scratch[0].as<int32_t>();
+        P.work_eps = c->scratch[2].as<double>();
+        P.n_work = 1;
+        P.sr = c->slots.sr.as<double2>();
+        P.touched = c->slots.touched.as<int32_t>();
+        P.queue = c->slots.queue.as<int32_t>();
+        P.queue_cap = cap;
+        P.n_slots = 1;
+        P.counters = c->counters.as<unsigned long long>();
+        P.debug_keep = 1;
+        fill_rule_constants(P, rho);
+        ARCTE_TRY(launch_push(c, rule, P));
+        int64_t hc[PC_COUNT];
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+        const int64_t nt = hc[PC_TOUCHED];
+        double *s_dev = c->scratch[3].as<double>();
+        double *r_dev = s_dev + c->n;
+        if (hc[PC_OVERFLOW_SEEDS] == 0) {
+            k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0);
+            ++c->stats.launches;
+            ARCTE_CUDA_TRY(cudaMemcpyAsync(host_s, s_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
+            ARCTE_CUDA_TRY(cudaMemcpyAsync(host_r, r_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
+        }
+        if (nt > 0) {
+            k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1);
+            ++c->stats.launches;
+        }
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hc[PC_OVERFLOW_SEEDS] == 0) {
+            if (n_push) *n_push = hc[PC_PUSHES];
+            return ARCTE_OK;
+        }
+        // ring too small for this seed: the whole pool's ring area is ours (one walk)
+        const int64_t pool_entries = (int64_t)(c->slots.queue.bytes / sizeof(int32_t));
+        int64_t next = cap * 8;
+        if (next > pool_entries) {
+            int64_t p = 1;
+            while (p * 2 <= pool_entries) p *= 2;
+            next = p;
+        }
+        if (next <= cap || attempt > 8) {
+            set_error("push: FIFO ring cannot be grown further for this seed");
+            return ARCTE_E_OVERFLOW;
+        }
+        cap = next;
+        ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
+    }
+}
+
+}  // namespace arcte

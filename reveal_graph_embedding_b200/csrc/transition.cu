@@ -1,0 +1,281 @@
+// transition.cu -- K1 (degrees + row normalisation), K2a (seed selection/ordering) and
+// K2b (epsilon-effective per seed).
+//
+// Reference being replaced (paths relative to /root/reference/reveal_graph_embedding/):
+//   K1   get_natural_random_walk_matrix        eps_randomwalk/transition.py:43-68
+//   K2a  seed list in arcte()                  embedding/arcte/arcte.py:610-617
+//   K2b  calculate_epsilon_effective           embedding/arcte/arcte.py:26-50
+//
+// Bit-exactness notes.  The degree vectors are scipy.sparse sums whose rounding depends
+// on the order of the additions; both orders are reproduced exactly (see oracle/
+// arcte_oracle.c, oracle_transition):
+//   out_degree[i] = data[first] + numpy_pairwise_sum(data[first+1 : end])   (add.reduceat)
+//   in_degree[c]  = ((0 + a_{r1,c}) + a_{r2,c}) + ...  rows ascending       (CSC mat-vec)
+// The second needs the column's entries in row order, i.e. a transposition; it is done
+// with the stable radix sort (key = column, value = weight) so no atomics on doubles and
+// no run-to-run variation.
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace arcte {
+
+// ---- K1a: out-degree, one thread per row ----------------------------------------------
+__global__ void __launch_bounds__(256)
+k_row_degree(int64_t n, const int64_t *__restrict__ indptr, const double *__restrict__ adj,
+             double *__restrict__ d_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t b = indptr[i], e = indptr[i + 1];
+    double sum = 0.0;
+    if (e > b) {
+        sum = adj[b];
+        if (e - b > 1) {
+            auto at = [adj](int64_t j) { return adj[j]; };
+            sum = __dadd_rn(sum, pairwise_sum(at, b + 1, e - b - 1));
+        }
+    }
+    if (sum == 0.0) sum = 1.0;  // transition.py:58
+    d_out[i] = sum;
+}
+
+// ---- K1b: binarised column counts + sort keys ------------------------------------------
+__global__ void __launch_bounds__(256)
+k_col_count(int64_t nnz, const int32_t *__restrict__ indices, int32_t *__restrict__ colcnt,
+            uint32_t *__restrict__ keys)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const int32_t c = indices[j];
+    keys[j] = (uint32_t)c;
+    atomicAdd(&colcnt[c], 1);
+}
+
+// ---- K1c: in-degree, one thread per column over the column-sorted weights ---------------
+__global__ void __launch_bounds__(256)
+k_col_degree(int64_t n, const int64_t *__restrict__ cscptr, const double *__restrict__ sorted_w,
+             double *__restrict__ d_in)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double y = 0.0;
+    for (int64_t j = cscptr[c]; j < cscptr[c + 1]; ++j) y = __dadd_rn(y, sorted_w[j]);
+    d_in[c] = y;
+}
+
+// ---- K1d: W = D_out^-1 A, one warp per row ------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_normalise(int64_t n, const int64_t *__restrict__ indptr, const double *__restrict__ adj,
+            const double *__restrict__ d_out, double *__restrict__ w)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const int64_t b = indptr[row], e = indptr[row + 1];
+    const double d = d_out[row];
+    for (int64_t j = b + lane_id(); j < e; j += 32) w[j] = __ddiv_rn(adj[j], d);  // transition.py:61-63
+}
+
+// ---- K2a: seed keys -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_count_stats(int64_t n, const int32_t *__restrict__ colcnt, int64_t *__restrict__ out /*[2]: max, n_seeds*/)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t c = i < n ? colcnt[i] : 0;
+    int is_seed = c > 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c = max(c, __shfl_xor_sync(kFull, c, o));
+        is_seed += __shfl_xor_sync(kFull, is_seed, o);
+    }
+    if (lane_id() == 0) {
+        atomicMax((unsigned long long *)&out[0], (unsigned long long)c);
+        if (is_seed) atomicAdd((unsigned long long *)&out[1], (unsigned long long)is_seed);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_seed_keys(int64_t n, const int32_t *__restrict__ colcnt, int32_t maxcnt, uint32_t *__restrict__ keys,
+            uint32_t *__restrict__ ids)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = colcnt[i];
+    // seeds (count > 1, arcte.py:617) sort by count descending; everything else goes last
+    keys[i] = c > 1 ? (uint32_t)(maxcnt - c) : (uint32_t)maxcnt;
+    ids[i] = (uint32_t)i;
+}
+
+// ---- K2b: epsilon-effective, one thread per seed --------------------------------------------
+__global__ void __launch_bounds__(128)
+k_eps_effective(int64_t n_seeds, const int32_t *__restrict__ seeds, double epsilon,
+                const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                const double *__restrict__ d_out, double *__restrict__ eps_out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_seeds) return;
+    const int32_t seed = seeds[k];
+    const int64_t b = indptr[seed], e = indptr[seed + 1];
+    const int64_t deg = e - b;
+    const double ds = d_out[seed];
+    auto at = [indices, d_out](int64_t j) { return d_out[indices[j]]; };
+    const double mean = __ddiv_rn(pairwise_sum(at, b, deg), (double)deg);  // arcte.py:32
+    double dmin = INFINITY, dmax = -INFINITY;
+    for (int64_t j = b; j < e; ++j) {
+        const double d = d_out[indices[j]];
+        dmin = fmin(dmin, d);
+        dmax = fmax(dmax, d);
+    }
+    // arcte.py:35
+    double eff = __ddiv_rn(__dmul_rn(epsilon, log(__dadd_rn(1.0, ds))), log(__dadd_rn(1.0, mean)));
+    const double hi = __ddiv_rn(1.0, __dmul_rn(ds, dmin));  // arcte.py:39
+    const double lo = __ddiv_rn(1.0, __dmul_rn(ds, dmax));  // arcte.py:40
+    if (eff > hi) eff = hi;                                       // arcte.py:45-46
+    else if (eff < lo) eff = __ddiv_rn(__dadd_rn(lo, eff), 2.0);  // arcte.py:47-48
+    eps_out[k] = eff;
+}
+
+static int bit_length(uint64_t v)
+{
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+static inline unsigned grid_for(int64_t items, int block) { return (unsigned)((items + block - 1) / block); }
+
+// ---- K2a: seeds, count-descending (ties: ascending node id); needs colcnt ----
+int select_seeds(arcte_cuda_ctx *c)
+{
+    const int64_t n = c->n;
+    cudaStream_t st = c->stream;
+    int64_t *launches = &c->stats.launches;
+    const size_t m = (size_t)n + 1;
+    ARCTE_TRY(dev_reserve(c->seeds, sizeof(int32_t) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[1], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * 2));
+    ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
+    int64_t *tmp2 = c->scratch[7].as<int64_t>();
+    ARCTE_CUDA_TRY(cudaMemsetAsync(tmp2, 0, 2 * sizeof(int64_t), st));
+    k_count_stats<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), tmp2);
+    ++*launches;
+    int64_t host2[2];
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(host2, tmp2, sizeof(host2), cudaMemcpyDeviceToHost, st));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    const int32_t maxcnt = (int32_t)host2[0];
+    c->n_seeds = host2[1];
+    k_seed_keys<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), maxcnt,
+                                                  c->scratch[0].as<uint32_t>(),
+                                                  (uint32_t *)c->scratch[2].p);
+    ++*launches;
+    bool second = false;
+    ARCTE_TRY(radix_sort_pairs(c->scratch[0].as<uint32_t>(), c->scratch[2].p,
+                               c->scratch[1].as<uint32_t>(), c->scratch[3].p, n,
+                               bit_length((uint64_t)maxcnt), 4, c->scratch[4], c->scratch[5],
+                               c->scratch[6], st, &second, launches));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->seeds.p, second ? c->scratch[3].p : c->scratch[2].p,
+                                   sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.ms_seeds = ms;
+    c->stats.n_seeds_total = c->n_seeds;
+    c->have_segments = false;
+    c->have_features = false;
+    return ARCTE_OK;
+}
+
+// Column counts only (used when the caller supplies W and the degrees itself).
+int count_columns(arcte_cuda_ctx *c)
+{
+    ARCTE_TRY(dev_reserve(c->colcnt, sizeof(int32_t) * (size_t)c->n));
+    ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * (size_t)((c->nnz > c->n ? c->nnz : c->n) + 1)));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->colcnt.p, 0, sizeof(int32_t) * (size_t)c->n, c->stream));
+    if (c->nnz > 0) {
+        k_col_count<<<grid_for(c->nnz, 256), 256, 0, c->stream>>>(c->nnz, c->indices.as<int32_t>(),
+                                                                  c->colcnt.as<int32_t>(),
+                                                                  c->scratch[0].as<uint32_t>());
+        ++c->stats.launches;
+    }
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    return ARCTE_OK;
+}
+
+int build_transition(arcte_cuda_ctx *c)
+{
+    if (!c->have_graph) { set_error("build_transition: no graph resident"); return ARCTE_E_ARG; }
+    const int64_t n = c->n, nnz = c->nnz;
+    cudaStream_t st = c->stream;
+    int64_t *launches = &c->stats.launches;
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
+
+    ARCTE_TRY(dev_reserve(c->w, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    ARCTE_TRY(dev_reserve(c->d_out, sizeof(double) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->d_in, sizeof(double) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->colcnt, sizeof(int32_t) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->seeds, sizeof(int32_t) * (size_t)n));
+
+    // scratch: [0] keys a, [1] keys b, [2] vals a, [3] vals b, [4] hist, [5] scan, [6] scan2, [7] cscptr
+    const size_t m = (size_t)(nnz > n ? nnz : n) + 1;
+    ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[1], sizeof(uint32_t) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(double) * m));
+    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * (size_t)(n + 2)));
+
+    k_row_degree<<<grid_for(n, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->adj.as<double>(),
+                                                   c->d_out.as<double>());
+    ++*launches;
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->colcnt.p, 0, sizeof(int32_t) * (size_t)n, st));
+    if (nnz > 0) {
+        k_col_count<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, c->indices.as<int32_t>(),
+                                                        c->colcnt.as<int32_t>(),
+                                                        c->scratch[0].as<uint32_t>());
+        ++*launches;
+    }
+    ARCTE_TRY(exclusive_scan_i32(c->colcnt.as<int32_t>(), c->scratch[7].as<int64_t>(), n,
+                                 c->scratch[6], st, launches));
+    // column-major order of the weights: stable sort by column keeps rows ascending
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[2].p, c->adj.p, sizeof(double) * (size_t)nnz,
+                                   cudaMemcpyDeviceToDevice, st));
+    bool second = false;
+    ARCTE_TRY(radix_sort_pairs(c->scratch[0].as<uint32_t>(), c->scratch[2].p,
+                               c->scratch[1].as<uint32_t>(), c->scratch[3].p, nnz,
+                               bit_length((uint64_t)(n > 0 ? n - 1 : 0)), 8, c->scratch[4],
+                               c->scratch[5], c->scratch[6], st, &second, launches));
+    const double *sorted_w = second ? c->scratch[3].as<double>() : c->scratch[2].as<double>();
+    k_col_degree<<<grid_for(n, 256), 256, 0, st>>>(n, c->scratch[7].as<int64_t>(), sorted_w,
+                                                   c->d_in.as<double>());
+    ++*launches;
+    k_normalise<<<grid_for(n * 32, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->adj.as<double>(),
+                                                       c->d_out.as<double>(), c->w.as<double>());
+    ++*launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
+
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.ms_transition = ms;
+    c->have_transition = true;
+    return select_seeds(c);
+}
+
+// eps_out[k] for seeds[k], both on the device.
+int compute_eps_effective(arcte_cuda_ctx *c, double epsilon, const int32_t *dev_seeds,
+                          int64_t n_seeds, double *dev_eps_out)
+{
+    if (n_seeds == 0) return ARCTE_OK;
+    k_eps_effective<<<grid_for(n_seeds, 128), 128, 0, c->stream>>>(
+        n_seeds, dev_seeds, epsilon, c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
+        c->d_out.as<double>(), dev_eps_out);
+    ++c->stats.launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    return ARCTE_OK;
+}
+
+}  // namespace arcte

@@ -1,0 +1,141 @@
+"""ARCTE feature extraction on B200 GPUs -- drop-in for
+reveal_graph_embedding/embedding/arcte/arcte.py of the reference.
+
+Same entry points, argument meaning and return value:
+
+    arcte(adjacency_matrix, rho, epsilon, number_of_threads=None)                  arcte.py:591
+    arcte_with_pagerank(adjacency_matrix, rho, epsilon, number_of_threads=None)    arcte.py:491
+    arcte_with_lazy_pagerank(adjacency_matrix, rho, epsilon, number_of_threads=None) arcte.py:391
+    arcte_worker(iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon)  arcte.py:279
+
+each returning the scipy.sparse CSR the reference returns (n x 2n, float64, canonical;
+the workers n x n).  `number_of_threads` used to be the size of the multiprocessing pool
+(arcte.py:650); here it caps the number of GPUs the seeds are sharded over (None = all
+visible GPUs).  Inside a torch.distributed job (one process per GPU, e.g. torchrun) every
+rank calls the function with the same matrix, processes its round-robin shard of the
+seeds and receives the full matrix after an NCCL all-gather of the per-GPU segments.
+
+Differences from the reference, all on purpose:
+  * no silent degradation: the reference prints and returns the base features when the
+    final hstack fails (arcte.py:684-686) and drops worker exceptions (arcte.py:657-666);
+    here every failure raises.
+  * number_of_threads larger than the number of seeds works (the reference crashes on an
+    empty chunk, arcte.py:19-23).
+"""
+import threading
+
+import numpy as np
+import scipy.sparse as sparse
+
+from ... import distributed
+from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, canonical_csr, device_count,
+                       get_engine)
+
+
+def _rule_rho(rule, rho):
+    # arcte.py:109: the lazy worker walks with lazy_rho, not rho
+    return (rho * 0.5) / (1 - (0.5 * rho)) if rule == RULE_LAZY else rho
+
+
+def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
+    A = canonical_csr(adjacency_matrix)
+    rho_eff = _rule_rho(rule, rho)
+
+    if distributed.is_active():
+        return distributed.arcte_distributed(A, rule, rho_eff, epsilon)
+
+    visible = device_count()
+    if visible < 1:
+        raise RuntimeError("arcte: no CUDA device visible (this package has no CPU path)")
+    n_gpus = visible if number_of_threads is None else max(1, min(int(number_of_threads), visible))
+
+    if n_gpus == 1:
+        eng = get_engine(0)
+        eng.set_graph(A, canonical=True)
+        eng.extract(rule, rho_eff, epsilon)
+        eng.assemble()
+        return eng.features()
+
+    # single process, several GPUs: graph replicated, seeds dealt round-robin (arcte.py:651),
+    # one host thread per GPU (ctypes drops the GIL), segments joined on GPU 0 by peer copies.
+    engines = [get_engine(d) for d in range(n_gpus)]
+    errors = []
+
+    def work(rank):
+        try:
+            e = engines[rank]
+            e.set_graph(A, canonical=True)
+            e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
+        except BaseException as exc:  # re-raised on the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(n_gpus)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    parts = []
+    for e in engines:
+        a, b, c, d = e.segments_device()
+        parts.append((e.n_segments, e.n_members, a, b, c, d))
+    engines[0].assemble(parts)
+    return engines[0].features()
+
+
+def arcte(adjacency_matrix, rho, epsilon, number_of_threads=None):
+    """Local-community features from absorbing regularised commute times (arcte.py:591-688)."""
+    return _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, RULE_ABSORBING)
+
+
+def arcte_with_pagerank(adjacency_matrix, rho, epsilon, number_of_threads=None):
+    """Same with personalised PageRank vectors (arcte.py:491-588)."""
+    return _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, RULE_PAGERANK)
+
+
+def arcte_with_lazy_pagerank(adjacency_matrix, rho, epsilon, number_of_threads=None):
+    """Same with lazy personalised PageRank vectors (arcte.py:391-488)."""
+    return _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, RULE_LAZY)
+
+
+def _worker(rule, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon):
+    eng = get_engine(0)
+    eng.set_transition(indptr_c, indices_c, data_c, out_degree, in_degree)
+    eng.set_seeds(np.asarray(iterate_nodes, dtype=np.int64))
+    eng.extract(rule, _rule_rho(rule, rho), epsilon)
+    eng.assemble()
+    n = eng.n
+    return sparse.csr_matrix(eng.features()[:, n:])
+
+
+def arcte_worker(iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon):
+    """The reference's per-process worker (arcte.py:279-388): n x n local-community block
+    for the given seed nodes, from the raw transition-matrix arrays."""
+    return _worker(RULE_ABSORBING, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon)
+
+
+def arcte_with_pagerank_worker(iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon):
+    """arcte.py:167-276."""
+    return _worker(RULE_PAGERANK, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon)
+
+
+def arcte_with_lazy_pagerank_worker(iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho,
+                                    epsilon):
+    """arcte.py:53-164."""
+    return _worker(RULE_LAZY, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon)
+
+
+def calculate_epsilon_effective(rho, epsilon, seed_degree, neighbor_degrees, mean_degree):
+    """arcte.py:26-50 on the GPU.  The reference signature works on bare degree values; the
+    device kernel works on a graph, so a star graph with those degrees is built on the fly
+    (node 0 = the seed).  Meant for parity tests, not for speed."""
+    nb = np.asarray(neighbor_degrees, dtype=np.float64)
+    k = nb.size
+    indptr = np.concatenate([[0, k], k + np.arange(1, k + 1)]).astype(np.int64)
+    indices = np.concatenate([np.arange(1, k + 1), np.zeros(k)]).astype(np.int32)
+    w = np.ones(2 * k)
+    d_out = np.concatenate([[float(seed_degree)], nb])
+    eng = get_engine(0)
+    eng.set_transition(indptr, indices, w, d_out, d_out.copy())
+    return float(eng.epsilon_effective(epsilon, [0])[0])

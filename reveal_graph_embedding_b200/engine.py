@@ -1,0 +1,216 @@
+"""Host-side driver of one GPU's libarcte_cuda context.
+
+`Engine` is a thin object over the C ABI (include/arcte_cuda.h): it owns one
+context (one GPU), converts scipy/numpy containers to the plain arrays the ABI
+takes and turns status codes into exceptions.  No computation happens here.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sparse
+
+from . import _lib
+from ._lib import RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, ArcteCudaError, check, ptr  # noqa: F401
+
+
+def canonical_csr(adjacency_matrix):
+    """What the reference feeds its workers: float64 CSR with sorted indices
+    (transition.py:52,65).  Duplicate entries are summed (the reference's numpy
+    fancy-index `+=` is ill-defined on them)."""
+    A = sparse.csr_matrix(adjacency_matrix, dtype=np.float64)  # no copy if already float64 CSR
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("adjacency matrix must be square, got %r" % (A.shape,))
+    if not A.has_canonical_format:
+        A = A.copy()  # never touch the caller's arrays
+        A.sum_duplicates()
+        A.sort_indices()
+    return A
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        check(self._L.arcte_cuda_create(C.byref(h), int(device)))
+        self._h = h
+        self.device = int(device)
+        self.n = 0
+        self.nnz = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.arcte_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -----------------------------------------------------------------
+    def configure(self, warps_per_sm=0, queue_capacity=0, mem_percent=0, member_capacity=0):
+        check(self._L.arcte_cuda_configure(self._h, int(warps_per_sm), int(queue_capacity), int(mem_percent),
+                                           int(member_capacity)))
+
+    # -- a11 + a1 -------------------------------------------------------------------------
+    def set_graph(self, adjacency_matrix, canonical=False):
+        """Upload the adjacency CSR and build the transition matrix (K1) and seed list (K2a)."""
+        A = adjacency_matrix if canonical else canonical_csr(adjacency_matrix)
+        self.n, self.nnz = int(A.shape[0]), int(A.nnz)
+        self._indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        self._indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+        self._data = np.ascontiguousarray(A.data, dtype=np.float64)
+        check(self._L.arcte_cuda_set_graph(self._h, self.n, self.nnz, ptr(self._indptr), ptr(self._indices),
+                                           ptr(self._data)))
+
+    def set_transition(self, indptr, indices, w, d_out, d_in):
+        """Upload W, out_degree, in_degree as given (arcte_worker's raw arrays, arcte.py:279-286)."""
+        self._indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self._indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self._data = np.ascontiguousarray(w, dtype=np.float64)
+        d_out = np.ascontiguousarray(d_out, dtype=np.float64)
+        d_in = np.ascontiguousarray(d_in, dtype=np.float64)
+        self.n, self.nnz = int(self._indptr.size - 1), int(self._indices.size)
+        if d_out.size != self.n or d_in.size != self.n or self._data.size != self.nnz:
+            raise ValueError("inconsistent transition arrays")
+        check(self._L.arcte_cuda_set_transition(self._h, self.n, self.nnz, ptr(self._indptr), ptr(self._indices),
+                                                ptr(self._data), ptr(d_out), ptr(d_in)))
+
+    def set_seeds(self, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+        check(self._L.arcte_cuda_set_seeds(self._h, seeds.size, ptr(seeds)))
+
+    def build_transition(self):
+        check(self._L.arcte_cuda_build_transition(self._h))
+
+    def transition(self):
+        """(W.data, out_degree, in_degree) like transition.py:99."""
+        w = np.empty(max(self.nnz, 1), dtype=np.float64)
+        d_out = np.empty(self.n, dtype=np.float64)
+        d_in = np.empty(self.n, dtype=np.float64)
+        check(self._L.arcte_cuda_get_transition(self._h, ptr(w), ptr(d_out), ptr(d_in)))
+        return w[:self.nnz], d_out, d_in
+
+    # -- a2 -----------------------------------------------------------------------------------
+    def seeds(self):
+        k = C.c_int64()
+        check(self._L.arcte_cuda_get_seed_count(self._h, C.byref(k)))
+        out = np.empty(max(k.value, 1), dtype=np.int64)
+        check(self._L.arcte_cuda_get_seeds(self._h, ptr(out)))
+        return out[:k.value]
+
+    # -- a4 -----------------------------------------------------------------------------------
+    def epsilon_effective(self, epsilon, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+        out = np.empty(max(seeds.size, 1), dtype=np.float64)
+        check(self._L.arcte_cuda_epsilon_effective(self._h, float(epsilon), seeds.size, ptr(seeds), ptr(out)))
+        return out[:seeds.size]
+
+    # -- a5-a7 ----------------------------------------------------------------------------------
+    def push(self, rule, seed, rho, eps_eff):
+        s = np.empty(self.n, dtype=np.float64)
+        r = np.empty(self.n, dtype=np.float64)
+        nop = C.c_int64()
+        check(self._L.arcte_cuda_push(self._h, int(rule), int(seed), float(rho), float(eps_eff), ptr(s), ptr(r),
+                                      C.byref(nop)))
+        return s, r, nop.value
+
+    # -- a3-a8 ----------------------------------------------------------------------------------
+    def extract(self, rule, rho, epsilon, shard_rank=0, shard_count=1, eps_override=None):
+        ov = None
+        if eps_override is not None:
+            ov = np.ascontiguousarray(eps_override, dtype=np.float64)
+        ns, nm = C.c_int64(), C.c_int64()
+        check(self._L.arcte_cuda_extract(self._h, int(rule), float(rho), float(epsilon), int(shard_rank),
+                                         int(shard_count), ptr(ov), C.byref(ns), C.byref(nm)))
+        self.n_segments, self.n_members = ns.value, nm.value
+        return ns.value, nm.value
+
+    def segments(self):
+        S, M = self.n_segments, self.n_members
+        seed = np.empty(max(S, 1), dtype=np.int32)
+        cnt = np.empty(max(S, 1), dtype=np.int32)
+        off = np.empty(max(S, 1), dtype=np.int64)
+        mem = np.empty(max(M, 1), dtype=np.int32)
+        check(self._L.arcte_cuda_get_segments(self._h, ptr(seed), ptr(cnt), ptr(off), ptr(mem)))
+        return seed[:S], cnt[:S], off[:S], mem[:M]
+
+    def segments_device(self):
+        """Raw device addresses (ints) of (seg_seed, seg_count, seg_offset, members)."""
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._L.arcte_cuda_segments_device(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value or 0, b.value or 0, c.value or 0, d.value or 0
+
+    def export_segments(self, seed_ptr, count_ptr, offset_ptr, members_ptr):
+        """D2D copy of the segments into caller-owned device buffers (addresses as ints)."""
+        check(self._L.arcte_cuda_export_segments(self._h, C.c_void_p(seed_ptr), C.c_void_p(count_ptr),
+                                                 C.c_void_p(offset_ptr), C.c_void_p(members_ptr)))
+
+    # -- a9-a10 ---------------------------------------------------------------------------------
+    def assemble(self, parts=None):
+        """parts: None (own segments) or a list of (n_segments, n_members, seed_ptr, count_ptr,
+        offset_ptr, members_ptr) with device addresses as ints."""
+        nnz = C.c_int64()
+        if not parts:
+            check(self._L.arcte_cuda_assemble(self._h, 0, None, None, None, None, None, None, C.byref(nnz)))
+        else:
+            P = len(parts)
+            ns = np.array([p[0] for p in parts], dtype=np.int64)
+            nm = np.array([p[1] for p in parts], dtype=np.int64)
+            cols = [np.array([p[i] for p in parts], dtype=np.uint64) for i in (2, 3, 4, 5)]
+            check(self._L.arcte_cuda_assemble(self._h, P, ptr(ns), ptr(nm), ptr(cols[0]), ptr(cols[1]),
+                                              ptr(cols[2]), ptr(cols[3]), C.byref(nnz)))
+        self.out_nnz = nnz.value
+        return nnz.value
+
+    def features(self):
+        """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
+        nnz = self.out_nnz
+        indptr = np.empty(self.n + 1, dtype=np.int64)
+        indices = np.empty(max(nnz, 1), dtype=np.int32)
+        data = np.empty(max(nnz, 1), dtype=np.float64)
+        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        indices = indices[:nnz]
+        data = data[:nnz]
+        if max(2 * self.n, nnz) < 2 ** 31:
+            indptr = indptr.astype(np.int32)
+        else:
+            indices = indices.astype(np.int64)
+        X = sparse.csr_matrix((data, indices, indptr), shape=(self.n, 2 * self.n), copy=False)
+        return X
+
+    def timer_start(self):
+        check(self._L.arcte_cuda_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(self._L.arcte_cuda_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(self._L.arcte_cuda_flush_l2(self._h))
+
+    def stats(self):
+        st = _lib.Stats()
+        check(self._L.arcte_cuda_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+
+_ENGINES = {}
+
+
+def get_engine(device=0):
+    """Process-wide engine per GPU: keeps the walk-state pool allocated between calls."""
+    e = _ENGINES.get(device)
+    if e is None or e._h is None:
+        e = Engine(device)
+        _ENGINES[device] = e
+    return e
+
+
+def device_count():
+    """Number of CUDA devices visible to the library (CUDA runtime, not torch)."""
+    n = C.c_int(0)
+    check(_lib.load().arcte_cuda_device_count(C.byref(n)))
+    return n.value
