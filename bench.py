@@ -228,13 +228,14 @@ def main():
         else:
             eng.assemble()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # NVML start-up happens during the warm-up, not inside the timed steps
     for _ in range(args.warmup):
         step()
     launches0 = eng.stats()["launches"]
-    sampler = ClockSampler(local_rank)
     step_ms, push_ms, alg_bytes, stage_ms = [], [], [], []
     barrier()
-    sampler.start()
+    sampler.lines.clear()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         eng.flush_l2()
@@ -315,6 +316,7 @@ def main():
             "stage_ms": dict(zip(("transition", "seeds_eps", "push_threshold", "assemble"),
                                  [float(x) for x in np.mean(np.array(stage_ms), axis=0)])),
             "features_nnz": int(nnz_out), "n_slots": st["n_slots"], "retries": st["retries"],
+            "slot_utilisation": st["slot_utilisation"],
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "timed_region_wall_s": wall}
     if e2e:

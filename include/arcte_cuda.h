@@ -72,6 +72,7 @@ typedef struct arcte_cuda_stats {
     double ms_push;          /* K3+K4: fused push / threshold / compaction kernel             */
     double ms_assemble;      /* K5: pack, transpose, splice                                    */
     double alg_bytes_push;   /* SURVEY 8(d) algorithmic bytes of the push kernel              */
+    double slot_utilisation; /* mean busy time of a walk state / span of the push launch      */
 } arcte_cuda_stats;
 
 /* -- lifetime ------------------------------------------------------------- */
@@ -128,6 +129,8 @@ int arcte_cuda_push(arcte_cuda_ctx *ctx, int rule, int64_t seed, double rho, dou
 /* -- a3 + a4-a8: extraction over a shard of the seed list -------------------- */
 /* arcte_worker (arcte.py:279-388) for seed-list positions shard_rank,
    shard_rank + shard_count, ... (roundrobin_chunks, arcte.py:19-23).
+   `rho` is the caller's restart probability; for ARCTE_RULE_LAZY the walk uses
+   lazy_rho = 0.5 rho / (1 - 0.5 rho) exactly like the reference worker (arcte.py:109).
    host_eps_override: NULL, or one epsilon-effective per GLOBAL seed-list position
    (parity seam).  Results stay on the device as segments. */
 int arcte_cuda_extract(arcte_cuda_ctx *ctx, int rule, double rho, double epsilon, int shard_rank,

@@ -31,7 +31,7 @@ class Stats(C.Structure):
         "n_seeds_total", "n_seeds_shard", "pushes", "edge_touches", "enqueues", "max_queue",
         "support", "touched", "seed_degree", "members", "emitted", "retries", "n_slots",
         "launches")] + [(k, C.c_double) for k in (
-            "ms_transition", "ms_seeds", "ms_push", "ms_assemble", "alg_bytes_push")]
+            "ms_transition", "ms_seeds", "ms_push", "ms_assemble", "alg_bytes_push", "slot_utilisation")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

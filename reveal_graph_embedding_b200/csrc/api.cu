@@ -116,7 +116,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->seeds,
+    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->seeds,
                       &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
                       &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->counters, &c->out_indptr,
                       &c->out_indices, &c->out_data};
@@ -160,6 +160,7 @@ static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int
         return ARCTE_E_ARG;
     }
     if (n >= (int64_t(1) << 30)) { set_error("graph upload: n must be < 2^30"); return ARCTE_E_ARG; }
+    if (nnz >= (int64_t(1) << 32)) { set_error("graph upload: nnz must be < 2^32"); return ARCTE_E_ARG; }
     if (host_indptr[0] != 0 || host_indptr[n] != nnz) {
         set_error("graph upload: indptr[0] must be 0 and indptr[n] must equal nnz");
         return ARCTE_E_ARG;

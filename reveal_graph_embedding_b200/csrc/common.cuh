@@ -42,6 +42,14 @@ struct DevBuf {
 int dev_reserve(DevBuf &b, size_t bytes);  // grow-only, contents not preserved
 void dev_free(DevBuf &b);
 
+// Immutable per-node record read on every pop and every neighbour touch: one 16-byte load
+// gives the in-degree and the CSR row of the node.
+struct __align__(16) NodeInfo {
+    double d_in;
+    uint32_t begin;  // indptr[v]
+    uint32_t len;    // indptr[v+1] - indptr[v]
+};
+
 // Per-seed walk state of one warp ("slot"): interleaved {s, r} pairs over all n
 // nodes (always all-zero between seeds), the touched list and the FIFO ring.
 struct SlotPool {
@@ -57,7 +65,8 @@ struct SlotPool {
 // Device-side counters of the fused push kernel (one int64 each, atomically added).
 enum PushCounter {
     PC_PUSHES = 0, PC_EDGES, PC_ENQUEUES, PC_MAXQ, PC_SUPPORT, PC_TOUCHED, PC_SEEDDEG, PC_MEMBERS,
-    PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR, PC_COUNT
+    PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR,
+    PC_T_START, PC_T_END, PC_T_BUSY, PC_COUNT
 };
 
 }  // namespace arcte
@@ -85,6 +94,7 @@ struct arcte_cuda_ctx {
     arcte::DevBuf d_out;    // double [n]
     arcte::DevBuf d_in;     // double [n]
     arcte::DevBuf colcnt;   // int32 [n]  binarised column counts
+    arcte::DevBuf node_info; // NodeInfo [n]
     bool have_graph = false, have_transition = false;
 
     // seeds
@@ -131,38 +141,70 @@ __device__ __forceinline__ unsigned lanemask_lt()
 // numpy's DOUBLE_pairwise_sum over n values produced by `at(i)`: identical tree and
 // therefore identical rounding to np.add.reduce on a contiguous float64 array
 // (blocks of <=128 elements with 8 strided accumulators, halves split on multiples of 8).
-template <typename F> __device__ double pairwise_sum(F at, int64_t off, int64_t n)
+template <typename F> __device__ __forceinline__ double pairwise_leaf(F at, int64_t off, int64_t n)
 {
     if (n < 8) {
         double res = 0.0;
         for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, at(off + i));
         return res;
-    } else if (n <= 128) {
-        double r0 = at(off + 0), r1 = at(off + 1), r2 = at(off + 2), r3 = at(off + 3);
-        double r4 = at(off + 4), r5 = at(off + 5), r6 = at(off + 6), r7 = at(off + 7);
-        int64_t i;
-        const int64_t lim = n - (n % 8);
-        for (i = 8; i < lim; i += 8) {
-            r0 = __dadd_rn(r0, at(off + i + 0));
-            r1 = __dadd_rn(r1, at(off + i + 1));
-            r2 = __dadd_rn(r2, at(off + i + 2));
-            r3 = __dadd_rn(r3, at(off + i + 3));
-            r4 = __dadd_rn(r4, at(off + i + 4));
-            r5 = __dadd_rn(r5, at(off + i + 5));
-            r6 = __dadd_rn(r6, at(off + i + 6));
-            r7 = __dadd_rn(r7, at(off + i + 7));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
-                               __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
-        for (; i < n; ++i) res = __dadd_rn(res, at(off + i));
-        return res;
-    } else {
-        int64_t n2 = n / 2;
-        n2 -= n2 % 8;
-        const double a = pairwise_sum(at, off, n2);
-        const double b = pairwise_sum(at, off + n2, n - n2);
-        return __dadd_rn(a, b);
     }
+    double r0 = at(off + 0), r1 = at(off + 1), r2 = at(off + 2), r3 = at(off + 3);
+    double r4 = at(off + 4), r5 = at(off + 5), r6 = at(off + 6), r7 = at(off + 7);
+    int64_t i;
+    const int64_t lim = n - (n % 8);
+    for (i = 8; i < lim; i += 8) {
+        r0 = __dadd_rn(r0, at(off + i + 0));
+        r1 = __dadd_rn(r1, at(off + i + 1));
+        r2 = __dadd_rn(r2, at(off + i + 2));
+        r3 = __dadd_rn(r3, at(off + i + 3));
+        r4 = __dadd_rn(r4, at(off + i + 4));
+        r5 = __dadd_rn(r5, at(off + i + 5));
+        r6 = __dadd_rn(r6, at(off + i + 6));
+        r7 = __dadd_rn(r7, at(off + i + 7));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; ++i) res = __dadd_rn(res, at(off + i));
+    return res;
+}
+
+// The recursion of the numpy routine (n > 128: split at n/2 rounded down to a multiple of
+// 8, left + right) unrolled into an explicit post-order walk: no device-side recursion, so
+// the stack need is static.  Depth <= 32 covers any n < 2^38.
+template <typename F> __device__ double pairwise_sum(F at, int64_t off, int64_t n)
+{
+    if (n <= 128) return pairwise_leaf(at, off, n);
+    constexpr int kDepth = 32;
+    int64_t f_off[kDepth], f_n[kDepth];
+    double f_left[kDepth];
+    signed char f_phase[kDepth];
+    int sp = 0;
+    f_off[0] = off; f_n[0] = n; f_phase[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int64_t o = f_off[sp], m = f_n[sp];
+        if (m <= 128) {
+            ret = pairwise_leaf(at, o, m);
+            --sp;
+            continue;
+        }
+        int64_t n2 = m / 2;
+        n2 -= n2 % 8;
+        if (f_phase[sp] == 0) {          // descend left
+            f_phase[sp] = 1;
+            ++sp;
+            f_off[sp] = o; f_n[sp] = n2; f_phase[sp] = 0;
+        } else if (f_phase[sp] == 1) {   // left done, descend right
+            f_left[sp] = ret;
+            f_phase[sp] = 2;
+            ++sp;
+            f_off[sp] = o + n2; f_n[sp] = m - n2; f_phase[sp] = 0;
+        } else {                         // both done
+            ret = __dadd_rn(f_left[sp], ret);
+            --sp;
+        }
+    }
+    return ret;
 }
 
 }  // namespace arcte

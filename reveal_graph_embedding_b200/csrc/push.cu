@@ -26,10 +26,9 @@ namespace arcte {
 
 struct PushParams {
     int64_t n;
-    const int64_t *indptr;
+    const NodeInfo *info;      // {d_in, row begin, row length} per node
     const int32_t *indices;
     const double *w;
-    const double *d_in;
     // work list
     const int32_t *work_seed;  // [n_work_total] seed node per position
     const double *work_eps;    // [n_work_total]
@@ -63,27 +62,35 @@ __device__ __forceinline__ double warp_min(double v)
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
     return v;
 }
-__device__ __forceinline__ int64_t warp_sum(int64_t v)
+__device__ __forceinline__ int warp_sum_i(int v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
 
-// Walk state of the warp for the current seed.
+// Per-warp statistics live in shared memory (no registers held across the walk).
+enum WarpStat { WS_PUSHES = 0, WS_EDGES, WS_ENQ, WS_MAXQ, WS_SUPPORT, WS_TOUCHED, WS_SEEDDEG, WS_MEMBERS,
+                WS_EMITTED, WS_COUNT };
+
+// Walk state of the warp for the current seed (all lanes hold the same values).
 struct Walk {
-    int64_t head, tail;  // FIFO
-    int nt;              // touched count
-    int64_t pushes, edges, enq, maxq;
+    unsigned head, tail;   // FIFO positions (monotone; ring index = pos & mask)
+    int nt;                // touched count
+    unsigned pushes, enq, maxq;
+    unsigned long long edges;
 };
 
-// One push of node u whose state pair su was just read, then (scan) the enqueue scan.
-// Returns false when the FIFO ring would overflow (nothing is lost: caller aborts the seed).
+constexpr int kPushUnroll = 2;  // neighbour chunks (of 32) in flight per warp
+
+// One push of node u (row [begin, begin+len), state pair su just read), then -- when
+// `scan` -- the enqueue scan over the same neighbours (similarity.py:194-196 / :214-216).
+// Returns false when the FIFO ring would overflow (the caller aborts and retries the seed).
 template <int RULE>
 __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restrict__ sr,
                                           int32_t *__restrict__ touched, int32_t *__restrict__ queue,
-                                          Walk &wk, int u, double2 su, double eps, bool scan, int lane,
-                                          unsigned lt)
+                                          Walk &wk, int u, double2 su, unsigned begin, unsigned len,
+                                          double eps, bool scan, int lane, unsigned lt)
 {
     double c;
     if (RULE == ARCTE_RULE_ABSORBING) {
@@ -100,41 +107,76 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
         if (lane == 0) sr[u] = make_double2(__dadd_rn(su.x, a), keep);  // push.py:34-35
     }
     __syncwarp();
-    const int64_t b = P.indptr[u], e = P.indptr[u + 1];
     wk.pushes += 1;
-    wk.edges += e - b;
-    const int64_t qmask = P.queue_cap - 1;
-    for (int64_t j0 = b; j0 < e; j0 += 32) {
-        const int64_t j = j0 + lane;
-        int v = 0;
-        bool is_new = false, enq = false;
-        if (j < e) {
-            v = P.indices[j];
-            const double p = __dmul_rn(c, P.w[j]);
-            const double2 o = sr[v];
-            double2 nw;
-            if (RULE == ARCTE_RULE_ABSORBING) {
-                nw.x = __dadd_rn(o.x, p);  // push.py:63
-                nw.y = __dadd_rn(o.y, p);  // push.py:64
-            } else {
-                nw.x = o.x;
-                nw.y = __dadd_rn(o.y, p);  // push.py:17 / :38
+    wk.edges += len;
+    const unsigned qmask = (unsigned)P.queue_cap - 1u;
+    const int32_t *__restrict__ idx = P.indices + begin;
+    const double *__restrict__ wgt = P.w + begin;
+    for (unsigned base = 0; base < len; base += 32 * kPushUnroll) {
+        // phase 1: neighbour ids and transition weights of up to kPushUnroll chunks
+        int v[kPushUnroll];
+        double p[kPushUnroll];
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k) {
+            const unsigned j = base + k * 32 + lane;
+            v[k] = -1;
+            if (j < len) {
+                v[k] = idx[j];
+                p[k] = __dmul_rn(c, wgt[j]);
             }
-            sr[v] = nw;
-            is_new = (o.x == 0.0 && o.y == 0.0) && (nw.x != 0.0 || nw.y != 0.0);
-            if (scan) enq = __ddiv_rn(nw.y, P.d_in[v]) >= eps;  // similarity.py:194 / :214
         }
-        const unsigned m_new = __ballot_sync(kFull, is_new);
-        if (is_new) touched[wk.nt + __popc(m_new & lt)] = v;
-        wk.nt += __popc(m_new);
+        // phase 2: their state pairs and in-degrees (independent gathers, all in flight)
+        double2 o[kPushUnroll];
+        double dv[kPushUnroll];
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k) {
+            if (v[k] >= 0) {
+                o[k] = sr[v[k]];
+                dv[k] = P.info[v[k]].d_in;
+            }
+        }
+        // phase 3: update and store (neighbours of one node are distinct: no ordering needed)
+        unsigned f_new = 0, f_enq = 0;  // per-lane flag bits, one per chunk
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k) {
+            if (v[k] >= 0) {
+                double2 nw;
+                if (RULE == ARCTE_RULE_ABSORBING) {
+                    nw.x = __dadd_rn(o[k].x, p[k]);  // push.py:63
+                    nw.y = __dadd_rn(o[k].y, p[k]);  // push.py:64
+                } else {
+                    nw.x = o[k].x;
+                    nw.y = __dadd_rn(o[k].y, p[k]);  // push.py:17 / :38
+                }
+                sr[v[k]] = nw;
+                if ((o[k].x == 0.0 && o[k].y == 0.0) && (nw.x != 0.0 || nw.y != 0.0)) f_new |= 1u << k;
+                if (scan && __ddiv_rn(nw.y, dv[k]) >= eps) f_enq |= 1u << k;  // similarity.py:194 / :214
+            }
+        }
+        // phase 4: ordered appends (CSR order = chunk order, then lane order).  Every node
+        // touched above is recorded BEFORE the ring can report overflow, so an aborted walk
+        // can always be undone through the touched list.
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k) {
+            if (base + k * 32 >= len) break;  // warp-uniform
+            const bool is_new = (f_new >> k) & 1u;
+            const unsigned m_new = __ballot_sync(kFull, is_new);
+            if (is_new) touched[wk.nt + __popc(m_new & lt)] = v[k];
+            wk.nt += __popc(m_new);
+        }
         if (scan) {
-            const unsigned m_enq = __ballot_sync(kFull, enq);
-            const int cnt = __popc(m_enq);
-            if (cnt) {
-                if (wk.tail - wk.head + cnt > P.queue_cap) return false;
-                if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = v;  // CSR order
-                wk.tail += cnt;
-                wk.enq += cnt;
+#pragma unroll
+            for (int k = 0; k < kPushUnroll; ++k) {
+                if (base + k * 32 >= len) break;  // warp-uniform
+                const bool enq = (f_enq >> k) & 1u;
+                const unsigned m_enq = __ballot_sync(kFull, enq);
+                const unsigned cnt = __popc(m_enq);
+                if (cnt) {
+                    if (wk.tail - wk.head + cnt > (unsigned)P.queue_cap) return false;
+                    if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = v[k];
+                    wk.tail += cnt;
+                    wk.enq += cnt;
+                }
             }
         }
     }
@@ -143,21 +185,28 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
     return true;
 }
 
+constexpr int kEpiUnroll = 4;  // touched entries per lane in flight in the threshold sweep
+
 template <int RULE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_push_threshold(const PushParams P)
 {
+    __shared__ unsigned long long wstat[8][WS_COUNT];
     const int lane = lane_id();
+    const int wib = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= P.n_slots) return;
     double2 *__restrict__ sr = P.sr + slot * P.n;
     int32_t *__restrict__ touched = P.touched + slot * P.n;
     int32_t *__restrict__ queue = P.queue + slot * P.queue_cap;
-    const int64_t qmask = P.queue_cap - 1;
+    const unsigned qmask = (unsigned)P.queue_cap - 1u;
+    unsigned long long *ws = wstat[wib];
+    if (lane < WS_COUNT) ws[lane] = 0ull;
+    __syncwarp();
 
-    int64_t a_pushes = 0, a_edges = 0, a_enq = 0, a_maxq = 0, a_support = 0, a_touched = 0;
-    int64_t a_seeddeg = 0, a_members = 0, a_emitted = 0;
+    unsigned long long t_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
     for (;;) {
         unsigned long long k = 0;
@@ -167,11 +216,13 @@ k_push_threshold(const PushParams P)
         const int64_t pos = P.work_ids ? (int64_t)P.work_ids[k] : (int64_t)k;
         const int seed = P.work_seed[pos];
         const double eps = P.work_eps[pos];
+        const NodeInfo seed_info = P.info[seed];
 
         Walk wk;
         wk.head = wk.tail = 0;
-        wk.nt = 0;
-        wk.pushes = wk.edges = wk.enq = wk.maxq = 0;
+        wk.nt = 1;
+        wk.pushes = wk.enq = wk.maxq = 0;
+        wk.edges = 0;
 
         // similarity.py:176-177 (absorbing) / :26, :84 (pagerank variants)
         double2 su = make_double2(RULE == ARCTE_RULE_ABSORBING ? 1.0 : 0.0, 1.0);
@@ -179,34 +230,51 @@ k_push_threshold(const PushParams P)
             sr[seed] = su;
             touched[0] = seed;
         }
-        wk.nt = 1;
         __syncwarp();
 
         // "Do one push for free" + first enqueue scan (similarity.py:183-196)
-        bool ok = push_node<RULE>(P, sr, touched, queue, wk, seed, su, eps, true, lane, lt);
+        bool ok = push_node<RULE>(P, sr, touched, queue, wk, seed, su, seed_info.begin, seed_info.len, eps,
+                                  true, lane, lt);
         if (ok && RULE == ARCTE_RULE_LAZY) {
             // similarity.py:106-114: repeated self pushes of the seed, no enqueue scan
-            const double du = P.d_in[seed];
             su = sr[seed];
-            while (__ddiv_rn(su.y, du) >= eps) {
-                push_node<RULE>(P, sr, touched, queue, wk, seed, su, eps, false, lane, lt);
+            while (__ddiv_rn(su.y, seed_info.d_in) >= eps) {
+                push_node<RULE>(P, sr, touched, queue, wk, seed, su, seed_info.begin, seed_info.len, eps, false,
+                                lane, lt);
                 su = sr[seed];
             }
         }
-        // similarity.py:199-216
-        while (ok && wk.head < wk.tail) {
-            const int u = queue[wk.head & qmask];
+        // similarity.py:199-216.  The node record of the NEXT queue entry is fetched while the
+        // current one is being pushed (it is immutable, so the early load is always valid).
+        bool have_next = false;
+        int nu = 0;
+        NodeInfo ninfo;
+        ninfo.d_in = 1.0; ninfo.begin = 0; ninfo.len = 0;
+        while (ok && wk.head != wk.tail) {
+            int u;
+            NodeInfo iu;
+            if (have_next) {
+                u = nu;
+                iu = ninfo;
+            } else {
+                u = queue[wk.head & qmask];
+                iu = P.info[u];
+            }
             wk.head += 1;
-            const double du = P.d_in[u];
             su = sr[u];
-            if (__ddiv_rn(su.y, du) >= eps) {  // similarity.py:204
-                ok = push_node<RULE>(P, sr, touched, queue, wk, u, su, eps, true, lane, lt);
+            have_next = wk.head != wk.tail;
+            if (have_next) {
+                nu = queue[wk.head & qmask];
+                ninfo = P.info[nu];
+            }
+            if (__ddiv_rn(su.y, iu.d_in) >= eps) {  // similarity.py:204
+                ok = push_node<RULE>(P, sr, touched, queue, wk, u, su, iu.begin, iu.len, eps, true, lane, lt);
                 if (!ok) break;
             }
             if (RULE == ARCTE_RULE_LAZY) {  // similarity.py:134-142
                 su = sr[u];
-                while (__ddiv_rn(su.y, du) >= eps) {
-                    push_node<RULE>(P, sr, touched, queue, wk, u, su, eps, false, lane, lt);
+                while (__ddiv_rn(su.y, iu.d_in) >= eps) {
+                    push_node<RULE>(P, sr, touched, queue, wk, u, su, iu.begin, iu.len, eps, false, lane, lt);
                     su = sr[u];
                 }
             }
@@ -235,47 +303,86 @@ k_push_threshold(const PushParams P)
         }
 
         // ---------------- K4: threshold + membership (arcte.py:352-376) ----------------
-        const int64_t b = P.indptr[seed], e = P.indptr[seed + 1];
-        const int64_t base_size = (e - b) + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
+        const unsigned sb = seed_info.begin, sl = seed_info.len;
+        const int base_size = (int)sl + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
         bool emit = true;
         if (RULE != ARCTE_RULE_ABSORBING) {
             // arcte.py:129-133 / :241-245: intersect1d(base, support).size >= base.size
-            int64_t inside = 0;
-            for (int64_t j = b + lane; j < e; j += 32) {
-                const int v = P.indices[j];
+            int inside = 0;
+            for (unsigned j = lane; j < sl; j += 32) {
+                const int v = P.indices[sb + j];
                 inside += (v != seed && sr[v].x != 0.0);
             }
-            inside = warp_sum(inside) + (sr[seed].x != 0.0 ? 1 : 0);
+            inside = warp_sum_i(inside) + (sr[seed].x != 0.0 ? 1 : 0);
             emit = inside >= base_size;
         }
-        int64_t m = 0, support = 0;
         double tau = 0.0;
         if (emit) {
             double q = INFINITY;
-            for (int64_t j = b + lane; j < e; j += 32) {
-                const int v = P.indices[j];
-                q = fmin(q, __ddiv_rn(sr[v].x, P.d_in[v]));  // arcte.py:355-356
+            for (unsigned j0 = 0; j0 < sl; j0 += 128) {
+                int v[4];
+                double2 o[4];
+                double d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned j = j0 + k * 32 + lane;
+                    v[k] = j < sl ? P.indices[sb + j] : -1;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (v[k] >= 0) {
+                        o[k] = sr[v[k]];
+                        d[k] = P.info[v[k]].d_in;
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (v[k] >= 0) q = fmin(q, __ddiv_rn(o[k].x, d[k]));  // arcte.py:355-356
             }
-            q = fmin(q, __ddiv_rn(sr[seed].x, P.d_in[seed]));
+            q = fmin(q, __ddiv_rn(sr[seed].x, seed_info.d_in));
             tau = warp_min(q);  // arcte.py:359-360
         }
-        // count of support entries with q >= tau (arcte.py:363-367; searchsorted 'left')
-        for (int i0 = 0; i0 < wk.nt; i0 += 32) {
-            const int i = i0 + lane;
-            bool in_sup = false, pass = false;
-            if (i < wk.nt) {
-                const int x = touched[i];
-                const double sx = sr[x].x;
-                in_sup = sx != 0.0;
-                pass = emit && in_sup && (__ddiv_rn(sx, P.d_in[x]) >= tau);
+        // One sweep over the touched list: count the support, keep (compacted in place, in
+        // list order) the nodes with s/d_in >= tau -- arcte.py:363-367, searchsorted 'left' --
+        // and zero the state (the sparse form of s[:]=0; r[:]=0, arcte.py:337-338).
+        int m = 0, support = 0;
+        for (int i0 = 0; i0 < wk.nt; i0 += 32 * kEpiUnroll) {
+            int x[kEpiUnroll];
+            double sx[kEpiUnroll], dx[kEpiUnroll];
+#pragma unroll
+            for (int k = 0; k < kEpiUnroll; ++k) {
+                const int i = i0 + k * 32 + lane;
+                x[k] = i < wk.nt ? touched[i] : -1;
             }
-            support += __popc(__ballot_sync(kFull, in_sup));
-            m += __popc(__ballot_sync(kFull, pass));
+#pragma unroll
+            for (int k = 0; k < kEpiUnroll; ++k) {
+                if (x[k] >= 0) {
+                    sx[k] = sr[x[k]].x;
+                    dx[k] = P.info[x[k]].d_in;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kEpiUnroll; ++k) {
+                if (i0 + k * 32 >= wk.nt) break;  // warp-uniform
+                bool in_sup = false, pass = false;
+                if (x[k] >= 0) {
+                    sr[x[k]] = make_double2(0.0, 0.0);
+                    in_sup = sx[k] != 0.0;
+                    pass = emit && in_sup && (__ddiv_rn(sx[k], dx[k]) >= tau);
+                }
+                support += __popc(__ballot_sync(kFull, in_sup));
+                if (emit) {
+                    const unsigned mp = __ballot_sync(kFull, pass);
+                    if (pass) touched[m + __popc(mp & lt)] = x[k];
+                    m += __popc(mp);
+                }
+            }
         }
+        __syncwarp();
         emit = emit && (m > base_size);  // arcte.py:370
-        int64_t off = 0;
         bool write = false;
         if (emit) {
+            int64_t off;
             if (P.retry_pass && P.seg_count[pos] > 0) {
                 off = P.seg_offset[pos];  // offset was assigned in the pass that overflowed
             } else {
@@ -284,8 +391,10 @@ k_push_threshold(const PushParams P)
                 off = (int64_t)__shfl_sync(kFull, o, 0);
             }
             write = off + m <= P.member_cap;
+            if (write)
+                for (int i = lane; i < m; i += 32) P.members[off + i] = touched[i];  // arcte.py:372-376
             if (lane == 0) {
-                P.seg_count[pos] = (int32_t)m;
+                P.seg_count[pos] = m;
                 P.seg_offset[pos] = off;
                 if (!write) {
                     const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
@@ -296,46 +405,39 @@ k_push_threshold(const PushParams P)
             P.seg_count[pos] = 0;
             P.seg_offset[pos] = 0;
         }
-        // second sweep: compact the members (arcte.py:372-376) and reset the slot
-        int64_t written = 0;
-        for (int i0 = 0; i0 < wk.nt; i0 += 32) {
-            const int i = i0 + lane;
-            int x = 0;
-            bool pass = false;
-            if (i < wk.nt) {
-                x = touched[i];
-                if (write) {
-                    const double sx = sr[x].x;
-                    pass = sx != 0.0 && (__ddiv_rn(sx, P.d_in[x]) >= tau);
-                }
-                sr[x] = make_double2(0.0, 0.0);  // sparse form of s[:]=0; r[:]=0 (arcte.py:337-338)
-            }
-            if (write) {
-                const unsigned mp = __ballot_sync(kFull, pass);
-                if (pass) P.members[off + written + __popc(mp & lt)] = x;
-                written += __popc(mp);
-            }
-        }
         __syncwarp();
 
-        if (!emit || write) {  // a seed whose members did not fit is re-run and counted then
-            a_pushes += wk.pushes; a_edges += wk.edges; a_enq += wk.enq;
-            if (wk.maxq > a_maxq) a_maxq = wk.maxq;
-            a_support += support; a_touched += wk.nt; a_seeddeg += e - b;
-            if (emit) { a_members += m; a_emitted += 1; }
+        if (lane == 0 && (!emit || write)) {  // a seed whose members did not fit is re-run and counted then
+            ws[WS_PUSHES] += wk.pushes;
+            ws[WS_EDGES] += wk.edges;
+            ws[WS_ENQ] += wk.enq;
+            if (wk.maxq > ws[WS_MAXQ]) ws[WS_MAXQ] = wk.maxq;
+            ws[WS_SUPPORT] += support;
+            ws[WS_TOUCHED] += wk.nt;
+            ws[WS_SEEDDEG] += sl;
+            if (emit) {
+                ws[WS_MEMBERS] += m;
+                ws[WS_EMITTED] += 1;
+            }
         }
     }
 
     if (lane == 0 && !P.debug_keep) {
-        atomicAdd(&P.counters[PC_PUSHES], (unsigned long long)a_pushes);
-        atomicAdd(&P.counters[PC_EDGES], (unsigned long long)a_edges);
-        atomicAdd(&P.counters[PC_ENQUEUES], (unsigned long long)a_enq);
-        atomicMax(&P.counters[PC_MAXQ], (unsigned long long)a_maxq);
-        atomicAdd(&P.counters[PC_SUPPORT], (unsigned long long)a_support);
-        atomicAdd(&P.counters[PC_TOUCHED], (unsigned long long)a_touched);
-        atomicAdd(&P.counters[PC_SEEDDEG], (unsigned long long)a_seeddeg);
-        atomicAdd(&P.counters[PC_MEMBERS], (unsigned long long)a_members);
-        atomicAdd(&P.counters[PC_EMITTED], (unsigned long long)a_emitted);
+        atomicAdd(&P.counters[PC_PUSHES], ws[WS_PUSHES]);
+        atomicAdd(&P.counters[PC_EDGES], ws[WS_EDGES]);
+        atomicAdd(&P.counters[PC_ENQUEUES], ws[WS_ENQ]);
+        atomicMax(&P.counters[PC_MAXQ], ws[WS_MAXQ]);
+        atomicAdd(&P.counters[PC_SUPPORT], ws[WS_SUPPORT]);
+        atomicAdd(&P.counters[PC_TOUCHED], ws[WS_TOUCHED]);
+        atomicAdd(&P.counters[PC_SEEDDEG], ws[WS_SEEDDEG]);
+        atomicAdd(&P.counters[PC_MEMBERS], ws[WS_MEMBERS]);
+        atomicAdd(&P.counters[PC_EMITTED], ws[WS_EMITTED]);
+        // occupancy of the launch: when this warp started/finished and how long it was busy
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        atomicMin(&P.counters[PC_T_START], t_begin);
+        atomicMax(&P.counters[PC_T_END], t_end);
+        atomicAdd(&P.counters[PC_T_BUSY], t_end - t_begin);
     }
 }
 
@@ -439,6 +541,7 @@ static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64
     int64_t want = (int64_t)c->sm_count * wps;
     want = ((want + 7) / 8) * 8;
     int64_t qcap = c->queue_cap_cfg > 0 ? c->queue_cap_cfg : (c->n < 65536 ? c->n : 65536);
+    if (c->queue_cap_cfg <= 0 && qcap < 8192) qcap = 8192;
     if (qcap < 64) qcap = 64;
     qcap = pow2_at_least(qcap);
     if (want > ((n_work + 7) / 8) * 8) want = ((n_work + 7) / 8) * 8;
@@ -539,10 +642,9 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
 
     PushParams P{};
     P.n = c->n;
-    P.indptr = c->indptr.as<int64_t>();
+    P.info = c->node_info.as<NodeInfo>();
     P.indices = c->indices.as<int32_t>();
     P.w = c->w.as<double>();
-    P.d_in = c->d_in.as<double>();
     P.work_seed = c->work_seed.as<int32_t>();
     P.work_eps = c->work_eps.as<double>();
     P.work_ids = nullptr;
@@ -560,9 +662,11 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     P.retry_list = c->retry_list.as<int32_t>();
     P.counters = c->counters.as<unsigned long long>();
     P.debug_keep = 0;
-    fill_rule_constants(P, rho);
+    // arcte.py:109: the lazy worker walks with lazy_rho = 0.5 rho / (1 - 0.5 rho)
+    fill_rule_constants(P, rule == ARCTE_RULE_LAZY ? (rho * (0.5)) / (1.0 - (0.5 * rho)) : rho);
 
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.as<int64_t>() + PC_T_START, 0xff, sizeof(int64_t), st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->seg_count.p, 0, sizeof(int32_t) * (size_t)S, st));
     cudaEvent_t p0, p1;
     ARCTE_CUDA_TRY(cudaEventCreate(&p0));
@@ -580,6 +684,10 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, p0, p1));
     stt.ms_push = ms;
     stt.n_slots = n_slots;
+    // mean busy time of a walk state / span of the launch (1.0 = no idle tail)
+    stt.slot_utilisation = hc[PC_T_END] > hc[PC_T_START]
+                               ? (double)hc[PC_T_BUSY] / ((double)n_slots * (double)(hc[PC_T_END] - hc[PC_T_START]))
+                               : 0.0;
 
     // ---- retry passes: seeds whose FIFO ring or member range did not fit ----
     int rounds = 0;
@@ -691,10 +799,9 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
     for (int attempt = 0;; ++attempt) {
         PushParams P{};
         P.n = c->n;
-        P.indptr = c->indptr.as<int64_t>();
+        P.info = c->node_info.as<NodeInfo>();
         P.indices = c->indices.as<int32_t>();
         P.w = c->w.as<double>();
-        P.d_in = c->d_in.as<double>();
         P.work_seed = c->scratch[0].as<int32_t>();
         P.work_eps = c->scratch[2].as<double>();
         P.n_work = 1;
@@ -728,17 +835,18 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
             if (n_push) *n_push = hc[PC_PUSHES];
             return ARCTE_OK;
         }
-        // ring too small for this seed: the whole pool's ring area is ours (one walk)
-        const int64_t pool_entries = (int64_t)(c->slots.queue.bytes / sizeof(int32_t));
-        int64_t next = cap * 8;
-        if (next > pool_entries) {
-            int64_t p = 1;
-            while (p * 2 <= pool_entries) p *= 2;
-            next = p;
-        }
-        if (next <= cap || attempt > 8) {
+        // ring too small for this seed: one walk only, so give it one big ring
+        const int64_t next = cap * 8;
+        if (attempt > 10) {
             set_error("push: FIFO ring cannot be grown further for this seed");
             return ARCTE_E_OVERFLOW;
+        }
+        if ((size_t)next * sizeof(int32_t) > c->slots.queue.bytes) {
+            dev_free(c->slots.queue);
+            c->slots.queue_slots = 0;
+            ARCTE_TRY(dev_reserve(c->slots.queue, sizeof(int32_t) * (size_t)next));
+            c->slots.queue_cap = next;
+            c->slots.queue_slots = 1;  // the next plan_slots re-creates the per-slot rings
         }
         cap = next;
         ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));

@@ -7,8 +7,8 @@
 //   K2b  calculate_epsilon_effective           embedding/arcte/arcte.py:26-50
 //
 // Bit-exactness notes.  The degree vectors are scipy.sparse sums whose rounding depends
-// on the order of the additions; both orders are reproduced exactly (see oracle/
-// arcte_oracle.c, oracle_transition):
+// on the order of the additions; both orders are reproduced exactly ("K1"):
+//
 //   out_degree[i] = data[first] + numpy_pairwise_sum(data[first+1 : end])   (add.reduceat)
 //   in_degree[c]  = ((0 + a_{r1,c}) + a_{r2,c}) + ...  rows ascending       (CSC mat-vec)
 // The second needs the column's entries in row order, i.e. a transposition; it is done
@@ -73,6 +73,20 @@ k_normalise(int64_t n, const int64_t *__restrict__ indptr, const double *__restr
     const int64_t b = indptr[row], e = indptr[row + 1];
     const double d = d_out[row];
     for (int64_t j = b + lane_id(); j < e; j += 32) w[j] = __ddiv_rn(adj[j], d);  // transition.py:61-63
+}
+
+// ---- K1e: per-node record {d_in, row begin, row length} for the push kernel ----------------
+__global__ void __launch_bounds__(256)
+k_node_info(int64_t n, const int64_t *__restrict__ indptr, const double *__restrict__ d_in,
+            NodeInfo *__restrict__ info)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NodeInfo r;
+    r.d_in = d_in[i];
+    r.begin = (uint32_t)indptr[i];
+    r.len = (uint32_t)(indptr[i + 1] - indptr[i]);
+    info[i] = r;
 }
 
 // ---- K2a: seed keys -----------------------------------------------------------------------
@@ -149,6 +163,11 @@ int select_seeds(arcte_cuda_ctx *c)
     const int64_t n = c->n;
     cudaStream_t st = c->stream;
     int64_t *launches = &c->stats.launches;
+    // the node records depend on d_in, which is final by now on both upload paths
+    ARCTE_TRY(dev_reserve(c->node_info, sizeof(NodeInfo) * (size_t)n));
+    k_node_info<<<grid_for(n, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->d_in.as<double>(),
+                                                  c->node_info.as<NodeInfo>());
+    ++*launches;
     const size_t m = (size_t)n + 1;
     ARCTE_TRY(dev_reserve(c->seeds, sizeof(int32_t) * (size_t)n));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * m));

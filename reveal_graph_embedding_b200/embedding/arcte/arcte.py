@@ -32,14 +32,9 @@ from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, canonical_csr, 
                        get_engine)
 
 
-def _rule_rho(rule, rho):
-    # arcte.py:109: the lazy worker walks with lazy_rho, not rho
-    return (rho * 0.5) / (1 - (0.5 * rho)) if rule == RULE_LAZY else rho
-
-
 def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     A = canonical_csr(adjacency_matrix)
-    rho_eff = _rule_rho(rule, rho)
+    rho_eff = rho  # the lazy_rho substitution of arcte.py:109 happens inside the library
 
     if distributed.is_active():
         return distributed.arcte_distributed(A, rule, rho_eff, epsilon)
@@ -103,7 +98,7 @@ def _worker(rule, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_deg
     eng = get_engine(0)
     eng.set_transition(indptr_c, indices_c, data_c, out_degree, in_degree)
     eng.set_seeds(np.asarray(iterate_nodes, dtype=np.int64))
-    eng.extract(rule, _rule_rho(rule, rho), epsilon)
+    eng.extract(rule, rho, epsilon)
     eng.assemble()
     n = eng.n
     return sparse.csr_matrix(eng.features()[:, n:])

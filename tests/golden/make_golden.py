@@ -195,5 +195,35 @@ def main():
             os.path.getsize(path) / 1024))
 
 
+
+
+def cli_fixture():
+    """Edge list -> reference CLI pipeline (entry_points/arcte.py:62-84) -> feature file."""
+    import scipy.sparse as spsp
+    from reveal_graph_embedding.datautil.datarw import read_adjacency_matrix, write_features
+    rng = np.random.default_rng(77)
+    ids = rng.choice(np.arange(1000, 5000), size=120, replace=False)
+    lines = ["# a comment line", "#another\tcomment"]
+    for _ in range(420):
+        a, b = rng.choice(ids, size=2)
+        lines.append("%d\t%d\t%s" % (a, b, repr(float(rng.integers(1, 4)))))
+    edge_path = os.path.join(HERE, "cli_edges.tsv")
+    with open(edge_path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    A, node_to_id = read_adjacency_matrix(file_path=edge_path, separator="\t", undirected=False)
+    A = spsp.csr_matrix(A)
+    coo = spsp.coo_matrix(A)
+    np.savez_compressed(os.path.join(HERE, "cli_adjacency.npz"), row=coo.row, col=coo.col, data=coo.data,
+                        n=A.shape[0], node_ids=np.array([node_to_id[i] for i in range(A.shape[0])]))
+    A = (A + A.transpose()) / 2
+    X = ref_arcte.arcte(adjacency_matrix=A, rho=RHO, epsilon=EPS, number_of_threads=1)
+    X = spsp.csr_matrix(X)
+    write_features(file_path=os.path.join(HERE, "cli_features.tsv"), features=X, separator="\t",
+                   node_to_id=node_to_id)
+    print("cli fixture: n=%d nnz=%d features nnz=%d" % (A.shape[0], A.nnz, X.nnz))
+
+
 if __name__ == "__main__":
-    main()
+    if "--cli-only" not in sys.argv:
+        main()
+    cli_fixture()
