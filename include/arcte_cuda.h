@@ -162,6 +162,13 @@ int arcte_cuda_assemble(arcte_cuda_ctx *ctx, int n_parts, const int64_t *part_n_
 int arcte_cuda_get_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *host_indices,
                             double *host_data);
 
+/* -- page-locked host memory for results ------------------------------------- */
+/* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be
+   page-locked so the device-to-host copy runs at PCIe rate instead of through the
+   driver's staging buffer.  Not tied to a context. */
+int arcte_cuda_host_alloc(void **out, int64_t bytes);
+int arcte_cuda_host_free(void *p);
+
 /* -- measurement helpers ------------------------------------------------------ */
 /* CUDA events on the context's own stream (the stream every kernel of this library is
    launched on), so a caller can time a whole step on the device. */

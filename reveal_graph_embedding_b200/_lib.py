@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarcte_cuda.so")
+LIB_PATH = os.environ.get("ARCTE_CUDA_LIB") or os.path.join(_HERE, "libarcte_cuda.so")  # override: kernel experiments
 
 RULE_ABSORBING, RULE_PAGERANK, RULE_LAZY = 0, 1, 2
 
@@ -22,7 +22,7 @@ SYMBOLS = [
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
     "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
     "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_get_features",
-    "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
+    "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
         L.arcte_cuda_export_segments.argtypes = [vp, vp, vp, vp, vp]
         L.arcte_cuda_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
         L.arcte_cuda_get_features.argtypes = [vp, vp, vp, vp]
+        L.arcte_cuda_host_alloc.argtypes = [C.POINTER(vp), i64]
+        L.arcte_cuda_host_free.argtypes = [vp]
         L.arcte_cuda_timer_start.argtypes = [vp]
         L.arcte_cuda_timer_stop.argtypes = [vp, C.POINTER(dbl)]
         L.arcte_cuda_flush_l2.argtypes = [vp]

@@ -442,6 +442,20 @@ int arcte_cuda_get_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *ho
     return ARCTE_OK;
 }
 
+int arcte_cuda_host_alloc(void **out, int64_t bytes)
+{
+    if (!out || bytes <= 0) { set_error("host_alloc: bad arguments"); return ARCTE_E_ARG; }
+    *out = nullptr;
+    ARCTE_CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_host_free(void *p)
+{
+    if (p) ARCTE_CUDA_TRY(cudaFreeHost(p));
+    return ARCTE_OK;
+}
+
 int arcte_cuda_timer_start(arcte_cuda_ctx *c)
 {
     CHECK_CTX(c);

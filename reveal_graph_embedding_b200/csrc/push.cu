@@ -69,46 +69,61 @@ __device__ __forceinline__ int warp_sum_i(int v)
     return v;
 }
 
+// State pairs are gathered at random over gigabytes: keep them out of L1 (L2-only loads and
+// stores) so L1 stays with what is re-read -- the FIFO ring, the touched list, node records,
+// CSR rows and the few spilled registers.
+#ifndef ARCTE_STATE_L1
+__device__ __forceinline__ double2 ld_state(const double2 *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_state(double2 *p, double2 v) { __stcg(p, v); }
+#else
+__device__ __forceinline__ double2 ld_state(const double2 *p) { return *p; }
+__device__ __forceinline__ void st_state(double2 *p, double2 v) { *p = v; }
+#endif
+
 // Per-warp statistics live in shared memory (no registers held across the walk).
 enum WarpStat { WS_PUSHES = 0, WS_EDGES, WS_ENQ, WS_MAXQ, WS_SUPPORT, WS_TOUCHED, WS_SEEDDEG, WS_MEMBERS,
-                WS_EMITTED, WS_COUNT };
+                WS_EMITTED, WS_T_BEGIN, WS_COUNT };
 
 // Walk state of the warp for the current seed (all lanes hold the same values).
 struct Walk {
     unsigned head, tail;   // FIFO positions (monotone; ring index = pos & mask)
     int nt;                // touched count
-    unsigned pushes, enq, maxq;
-    unsigned long long edges;
 };
 
-constexpr int kPushUnroll = 2;  // neighbour chunks (of 32) in flight per warp
+#ifndef ARCTE_PUSH_UNROLL
+#define ARCTE_PUSH_UNROLL 1
+#endif
+constexpr int kPushUnroll = ARCTE_PUSH_UNROLL;  // neighbour chunks (of 32) in flight per warp
 
 // One push of node u (row [begin, begin+len), state pair su just read), then -- when
 // `scan` -- the enqueue scan over the same neighbours (similarity.py:194-196 / :214-216).
 // Returns false when the FIFO ring would overflow (the caller aborts and retries the seed).
+// ws: this warp's statistics row in shared memory (updated by lane 0 only).
 template <int RULE>
 __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restrict__ sr,
                                           int32_t *__restrict__ touched, int32_t *__restrict__ queue,
-                                          Walk &wk, int u, double2 su, unsigned begin, unsigned len,
-                                          double eps, bool scan, int lane, unsigned lt)
+                                          Walk &wk, unsigned long long *ws, int u, double2 su, unsigned begin,
+                                          unsigned len, double eps, bool scan, int lane, unsigned lt)
 {
     double c;
     if (RULE == ARCTE_RULE_ABSORBING) {
         c = __dmul_rn(P.one_minus_rho, su.y);            // push.py:57
-        if (lane == 0) sr[u] = make_double2(su.x, 0.0);  // push.py:60
+        if (lane == 0) st_state(&sr[u], make_double2(su.x, 0.0));  // push.py:60
     } else if (RULE == ARCTE_RULE_PAGERANK) {
         const double a = __dmul_rn(P.rho, su.y);          // push.py:9
         c = __dmul_rn(P.one_minus_rho, su.y);             // push.py:10
-        if (lane == 0) sr[u] = make_double2(__dadd_rn(su.x, a), 0.0);  // push.py:13-14
+        if (lane == 0) st_state(&sr[u], make_double2(__dadd_rn(su.x, a), 0.0));  // push.py:13-14
     } else {
         const double a = __dmul_rn(P.rho, su.y);          // push.py:29
         c = __dmul_rn(P.lazy_b, su.y);                    // push.py:30
         const double keep = __dmul_rn(P.lazy_c, su.y);    // push.py:31
-        if (lane == 0) sr[u] = make_double2(__dadd_rn(su.x, a), keep);  // push.py:34-35
+        if (lane == 0) st_state(&sr[u], make_double2(__dadd_rn(su.x, a), keep));  // push.py:34-35
+    }
+    if (lane == 0) {
+        ws[WS_PUSHES] += 1;
+        ws[WS_EDGES] += len;
     }
     __syncwarp();
-    wk.pushes += 1;
-    wk.edges += len;
     const unsigned qmask = (unsigned)P.queue_cap - 1u;
     const int32_t *__restrict__ idx = P.indices + begin;
     const double *__restrict__ wgt = P.w + begin;
@@ -131,7 +146,7 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
 #pragma unroll
         for (int k = 0; k < kPushUnroll; ++k) {
             if (v[k] >= 0) {
-                o[k] = sr[v[k]];
+                o[k] = ld_state(&sr[v[k]]);
                 dv[k] = P.info[v[k]].d_in;
             }
         }
@@ -148,7 +163,7 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
                     nw.x = o[k].x;
                     nw.y = __dadd_rn(o[k].y, p[k]);  // push.py:17 / :38
                 }
-                sr[v[k]] = nw;
+                st_state(&sr[v[k]], nw);
                 if ((o[k].x == 0.0 && o[k].y == 0.0) && (nw.x != 0.0 || nw.y != 0.0)) f_new |= 1u << k;
                 if (scan && __ddiv_rn(nw.y, dv[k]) >= eps) f_enq |= 1u << k;  // similarity.py:194 / :214
             }
@@ -175,25 +190,32 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
                     if (wk.tail - wk.head + cnt > (unsigned)P.queue_cap) return false;
                     if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = v[k];
                     wk.tail += cnt;
-                    wk.enq += cnt;
+                    if (lane == 0) ws[WS_ENQ] += cnt;
                 }
             }
         }
     }
-    if (wk.tail - wk.head > wk.maxq) wk.maxq = wk.tail - wk.head;
+    if (lane == 0 && wk.tail - wk.head > ws[WS_MAXQ]) ws[WS_MAXQ] = wk.tail - wk.head;
     __syncwarp();
     return true;
 }
 
-constexpr int kEpiUnroll = 4;  // touched entries per lane in flight in the threshold sweep
+#ifndef ARCTE_EPI_UNROLL
+#define ARCTE_EPI_UNROLL 2
+#endif
+constexpr int kEpiUnroll = ARCTE_EPI_UNROLL;  // touched entries per lane in flight in the threshold sweep
+
+#ifndef ARCTE_PUSH_MIN_BLOCKS
+#define ARCTE_PUSH_MIN_BLOCKS 4
+#endif
 
 template <int RULE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, ARCTE_PUSH_MIN_BLOCKS)
 k_push_threshold(const PushParams P)
 {
-    __shared__ unsigned long long wstat[8][WS_COUNT];
+    // per-warp statistics: [0] totals of the finished seeds, [1] the seed being walked
+    __shared__ unsigned long long wstat[8][2][WS_COUNT];
     const int lane = lane_id();
-    const int wib = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= P.n_slots) return;
@@ -201,88 +223,70 @@ k_push_threshold(const PushParams P)
     int32_t *__restrict__ touched = P.touched + slot * P.n;
     int32_t *__restrict__ queue = P.queue + slot * P.queue_cap;
     const unsigned qmask = (unsigned)P.queue_cap - 1u;
-    unsigned long long *ws = wstat[wib];
-    if (lane < WS_COUNT) ws[lane] = 0ull;
+    unsigned long long *wtot = wstat[threadIdx.x >> 5][0];
+    unsigned long long *ws = wstat[threadIdx.x >> 5][1];
+    if (lane < WS_COUNT) wtot[lane] = 0ull;
     __syncwarp();
 
-    unsigned long long t_begin;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    if (lane == 0) {
+        unsigned long long t_begin;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+        wtot[WS_T_BEGIN] = t_begin;
+    }
 
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(&P.counters[PC_WORK_CURSOR], 1ull);
         k = __shfl_sync(kFull, k, 0);
         if ((int64_t)k >= P.n_work) break;
-        const int64_t pos = P.work_ids ? (int64_t)P.work_ids[k] : (int64_t)k;
+        const int pos = P.work_ids ? P.work_ids[k] : (int)k;
         const int seed = P.work_seed[pos];
         const double eps = P.work_eps[pos];
-        const NodeInfo seed_info = P.info[seed];
 
         Walk wk;
         wk.head = wk.tail = 0;
         wk.nt = 1;
-        wk.pushes = wk.enq = wk.maxq = 0;
-        wk.edges = 0;
+        if (lane < WS_COUNT) ws[lane] = 0ull;
 
         // similarity.py:176-177 (absorbing) / :26, :84 (pagerank variants)
         double2 su = make_double2(RULE == ARCTE_RULE_ABSORBING ? 1.0 : 0.0, 1.0);
         if (lane == 0) {
-            sr[seed] = su;
+            st_state(&sr[seed], su);
             touched[0] = seed;
         }
         __syncwarp();
 
-        // "Do one push for free" + first enqueue scan (similarity.py:183-196)
-        bool ok = push_node<RULE>(P, sr, touched, queue, wk, seed, su, seed_info.begin, seed_info.len, eps,
-                                  true, lane, lt);
-        if (ok && RULE == ARCTE_RULE_LAZY) {
-            // similarity.py:106-114: repeated self pushes of the seed, no enqueue scan
-            su = sr[seed];
-            while (__ddiv_rn(su.y, seed_info.d_in) >= eps) {
-                push_node<RULE>(P, sr, touched, queue, wk, seed, su, seed_info.begin, seed_info.len, eps, false,
-                                lane, lt);
-                su = sr[seed];
-            }
-        }
-        // similarity.py:199-216.  The node record of the NEXT queue entry is fetched while the
-        // current one is being pushed (it is immutable, so the early load is always valid).
-        bool have_next = false;
-        int nu = 0;
-        NodeInfo ninfo;
-        ninfo.d_in = 1.0; ninfo.begin = 0; ninfo.len = 0;
-        while (ok && wk.head != wk.tail) {
-            int u;
-            NodeInfo iu;
-            if (have_next) {
-                u = nu;
-                iu = ninfo;
-            } else {
-                u = queue[wk.head & qmask];
-                iu = P.info[u];
-            }
-            wk.head += 1;
-            su = sr[u];
-            have_next = wk.head != wk.tail;
-            if (have_next) {
-                nu = queue[wk.head & qmask];
-                ninfo = P.info[nu];
-            }
-            if (__ddiv_rn(su.y, iu.d_in) >= eps) {  // similarity.py:204
-                ok = push_node<RULE>(P, sr, touched, queue, wk, u, su, iu.begin, iu.len, eps, true, lane, lt);
+        // The walk.  Iteration 0 is the seed's unconditional push ("Do one push for free",
+        // similarity.py:183-196); every later iteration pops the FIFO head and pushes it if
+        // its residual still passes (similarity.py:199-216).  (Fetching the next entry's node
+        // record one pop ahead was measured and dropped: the launch is bound by random DRAM
+        // sectors, not by this dependent load -- profiles/README.md.)
+        int u = seed;
+        NodeInfo iu = P.info[seed];
+        bool first = true, ok = true;
+        for (;;) {
+            if (first || __ddiv_rn(su.y, iu.d_in) >= eps) {  // similarity.py:204
+                ok = push_node<RULE>(P, sr, touched, queue, wk, ws, u, su, iu.begin, iu.len, eps, true, lane, lt);
                 if (!ok) break;
             }
-            if (RULE == ARCTE_RULE_LAZY) {  // similarity.py:134-142
-                su = sr[u];
+            first = false;
+            if (RULE == ARCTE_RULE_LAZY) {  // similarity.py:106-114 / :134-142: repeated pushes, no scan
+                su = ld_state(&sr[u]);
                 while (__ddiv_rn(su.y, iu.d_in) >= eps) {
-                    push_node<RULE>(P, sr, touched, queue, wk, u, su, iu.begin, iu.len, eps, false, lane, lt);
-                    su = sr[u];
+                    push_node<RULE>(P, sr, touched, queue, wk, ws, u, su, iu.begin, iu.len, eps, false, lane, lt);
+                    su = ld_state(&sr[u]);
                 }
             }
+            if (wk.head == wk.tail) break;
+u = queue[wk.head & qmask];
+            iu = P.info[u];
+            wk.head += 1;
+            su = ld_state(&sr[u]);
         }
 
         if (P.debug_keep) {
             if (lane == 0) {
-                P.counters[PC_PUSHES] = (unsigned long long)wk.pushes;
+                P.counters[PC_PUSHES] = ws[WS_PUSHES];
                 P.counters[PC_TOUCHED] = (unsigned long long)wk.nt;
                 P.counters[PC_OVERFLOW_SEEDS] = ok ? 0ull : 1ull;
             }
@@ -291,10 +295,10 @@ k_push_threshold(const PushParams P)
 
         if (!ok) {
             // FIFO ring too small: undo and hand the seed to the retry pass
-            for (int i = lane; i < wk.nt; i += 32) sr[touched[i]] = make_double2(0.0, 0.0);
+            for (int i = lane; i < wk.nt; i += 32) st_state(&sr[touched[i]], make_double2(0.0, 0.0));
             if (lane == 0) {
                 const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
-                P.retry_list[r] = (int32_t)pos;
+                P.retry_list[r] = pos;
                 atomicAdd(&P.counters[PC_QOVERFLOW], 1ull);
                 P.seg_count[pos] = -1;
             }
@@ -303,42 +307,41 @@ k_push_threshold(const PushParams P)
         }
 
         // ---------------- K4: threshold + membership (arcte.py:352-376) ----------------
-        const unsigned sb = seed_info.begin, sl = seed_info.len;
-        const int base_size = (int)sl + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
+        const NodeInfo si = P.info[seed];
+        const int base_size = (int)si.len + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
         bool emit = true;
         if (RULE != ARCTE_RULE_ABSORBING) {
             // arcte.py:129-133 / :241-245: intersect1d(base, support).size >= base.size
             int inside = 0;
-            for (unsigned j = lane; j < sl; j += 32) {
-                const int v = P.indices[sb + j];
-                inside += (v != seed && sr[v].x != 0.0);
+            for (unsigned j = lane; j < si.len; j += 32) {
+                const int v = P.indices[si.begin + j];
+                inside += (v != seed && ld_state(&sr[v]).x != 0.0);
             }
-            inside = warp_sum_i(inside) + (sr[seed].x != 0.0 ? 1 : 0);
+            inside = warp_sum_i(inside) + (ld_state(&sr[seed]).x != 0.0 ? 1 : 0);
             emit = inside >= base_size;
         }
         double tau = 0.0;
         if (emit) {
-            double q = INFINITY;
-            for (unsigned j0 = 0; j0 < sl; j0 += 128) {
-                int v[4];
-                double2 o[4];
-                double d[4];
+            double q = __ddiv_rn(ld_state(&sr[seed]).x, si.d_in);
+            for (unsigned j0 = 0; j0 < si.len; j0 += 64) {
+                int v[2];
+                double2 o[2];
+                double d[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned j = j0 + k * 32 + lane;
-                    v[k] = j < sl ? P.indices[sb + j] : -1;
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const unsigned j = j0 + k2 * 32 + lane;
+                    v[k2] = j < si.len ? P.indices[si.begin + j] : -1;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (v[k] >= 0) {
-                        o[k] = sr[v[k]];
-                        d[k] = P.info[v[k]].d_in;
+                for (int k2 = 0; k2 < 2; ++k2)
+                    if (v[k2] >= 0) {
+                        o[k2] = ld_state(&sr[v[k2]]);
+                        d[k2] = P.info[v[k2]].d_in;
                     }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (v[k] >= 0) q = fmin(q, __ddiv_rn(o[k].x, d[k]));  // arcte.py:355-356
+                for (int k2 = 0; k2 < 2; ++k2)
+                    if (v[k2] >= 0) q = fmin(q, __ddiv_rn(o[k2].x, d[k2]));  // arcte.py:355-356
             }
-            q = fmin(q, __ddiv_rn(sr[seed].x, seed_info.d_in));
             tau = warp_min(q);  // arcte.py:359-360
         }
         // One sweep over the touched list: count the support, keep (compacted in place, in
@@ -349,31 +352,31 @@ k_push_threshold(const PushParams P)
             int x[kEpiUnroll];
             double sx[kEpiUnroll], dx[kEpiUnroll];
 #pragma unroll
-            for (int k = 0; k < kEpiUnroll; ++k) {
-                const int i = i0 + k * 32 + lane;
-                x[k] = i < wk.nt ? touched[i] : -1;
+            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+                const int i = i0 + k2 * 32 + lane;
+                x[k2] = i < wk.nt ? touched[i] : -1;
             }
 #pragma unroll
-            for (int k = 0; k < kEpiUnroll; ++k) {
-                if (x[k] >= 0) {
-                    sx[k] = sr[x[k]].x;
-                    dx[k] = P.info[x[k]].d_in;
+            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+                if (x[k2] >= 0) {
+                    sx[k2] = ld_state(&sr[x[k2]]).x;
+                    dx[k2] = P.info[x[k2]].d_in;
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < kEpiUnroll; ++k) {
-                if (i0 + k * 32 >= wk.nt) break;  // warp-uniform
+            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+                if (i0 + k2 * 32 >= wk.nt) break;  // warp-uniform
                 bool in_sup = false, pass = false;
-                if (x[k] >= 0) {
-                    sr[x[k]] = make_double2(0.0, 0.0);
-                    in_sup = sx[k] != 0.0;
-                    pass = emit && in_sup && (__ddiv_rn(sx[k], dx[k]) >= tau);
+                if (x[k2] >= 0) {
+                    st_state(&sr[x[k2]], make_double2(0.0, 0.0));
+                    in_sup = sx[k2] != 0.0;
+                    pass = emit && in_sup && (__ddiv_rn(sx[k2], dx[k2]) >= tau);
                 }
                 support += __popc(__ballot_sync(kFull, in_sup));
                 if (emit) {
                     const unsigned mp = __ballot_sync(kFull, pass);
-                    if (pass) touched[m + __popc(mp & lt)] = x[k];
+                    if (pass) touched[m + __popc(mp & lt)] = x[k2];
                     m += __popc(mp);
                 }
             }
@@ -398,7 +401,7 @@ k_push_threshold(const PushParams P)
                 P.seg_offset[pos] = off;
                 if (!write) {
                     const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
-                    P.retry_list[r] = (int32_t)pos;
+                    P.retry_list[r] = pos;
                 }
             }
         } else if (lane == 0) {
@@ -408,36 +411,37 @@ k_push_threshold(const PushParams P)
         __syncwarp();
 
         if (lane == 0 && (!emit || write)) {  // a seed whose members did not fit is re-run and counted then
-            ws[WS_PUSHES] += wk.pushes;
-            ws[WS_EDGES] += wk.edges;
-            ws[WS_ENQ] += wk.enq;
-            if (wk.maxq > ws[WS_MAXQ]) ws[WS_MAXQ] = wk.maxq;
-            ws[WS_SUPPORT] += support;
-            ws[WS_TOUCHED] += wk.nt;
-            ws[WS_SEEDDEG] += sl;
+            wtot[WS_PUSHES] += ws[WS_PUSHES];
+            wtot[WS_EDGES] += ws[WS_EDGES];
+            wtot[WS_ENQ] += ws[WS_ENQ];
+            if (ws[WS_MAXQ] > wtot[WS_MAXQ]) wtot[WS_MAXQ] = ws[WS_MAXQ];
+            wtot[WS_SUPPORT] += support;
+            wtot[WS_TOUCHED] += wk.nt;
+            wtot[WS_SEEDDEG] += si.len;
             if (emit) {
-                ws[WS_MEMBERS] += m;
-                ws[WS_EMITTED] += 1;
+                wtot[WS_MEMBERS] += m;
+                wtot[WS_EMITTED] += 1;
             }
         }
+        __syncwarp();
     }
 
     if (lane == 0 && !P.debug_keep) {
-        atomicAdd(&P.counters[PC_PUSHES], ws[WS_PUSHES]);
-        atomicAdd(&P.counters[PC_EDGES], ws[WS_EDGES]);
-        atomicAdd(&P.counters[PC_ENQUEUES], ws[WS_ENQ]);
-        atomicMax(&P.counters[PC_MAXQ], ws[WS_MAXQ]);
-        atomicAdd(&P.counters[PC_SUPPORT], ws[WS_SUPPORT]);
-        atomicAdd(&P.counters[PC_TOUCHED], ws[WS_TOUCHED]);
-        atomicAdd(&P.counters[PC_SEEDDEG], ws[WS_SEEDDEG]);
-        atomicAdd(&P.counters[PC_MEMBERS], ws[WS_MEMBERS]);
-        atomicAdd(&P.counters[PC_EMITTED], ws[WS_EMITTED]);
+        atomicAdd(&P.counters[PC_PUSHES], wtot[WS_PUSHES]);
+        atomicAdd(&P.counters[PC_EDGES], wtot[WS_EDGES]);
+        atomicAdd(&P.counters[PC_ENQUEUES], wtot[WS_ENQ]);
+        atomicMax(&P.counters[PC_MAXQ], wtot[WS_MAXQ]);
+        atomicAdd(&P.counters[PC_SUPPORT], wtot[WS_SUPPORT]);
+        atomicAdd(&P.counters[PC_TOUCHED], wtot[WS_TOUCHED]);
+        atomicAdd(&P.counters[PC_SEEDDEG], wtot[WS_SEEDDEG]);
+        atomicAdd(&P.counters[PC_MEMBERS], wtot[WS_MEMBERS]);
+        atomicAdd(&P.counters[PC_EMITTED], wtot[WS_EMITTED]);
         // occupancy of the launch: when this warp started/finished and how long it was busy
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        atomicMin(&P.counters[PC_T_START], t_begin);
+        atomicMin(&P.counters[PC_T_START], wtot[WS_T_BEGIN]);
         atomicMax(&P.counters[PC_T_END], t_end);
-        atomicAdd(&P.counters[PC_T_BUSY], t_end - t_begin);
+        atomicAdd(&P.counters[PC_T_BUSY], t_end - wtot[WS_T_BEGIN]);
     }
 }
 

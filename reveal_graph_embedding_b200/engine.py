@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import scipy.sparse as sparse
 
-from . import _lib
+from . import _lib, hostmem
 from ._lib import RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, ArcteCudaError, check, ptr  # noqa: F401
 
 
@@ -168,8 +168,8 @@ class Engine:
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
         nnz = self.out_nnz
         indptr = np.empty(self.n + 1, dtype=np.int64)
-        indices = np.empty(max(nnz, 1), dtype=np.int32)
-        data = np.empty(max(nnz, 1), dtype=np.float64)
+        indices = hostmem.empty(max(nnz, 1), np.int32)   # page-locked for large results
+        data = hostmem.empty(max(nnz, 1), np.float64)
         check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
         indices = indices[:nnz]
         data = data[:nnz]

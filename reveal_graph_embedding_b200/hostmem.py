@@ -1,0 +1,103 @@
+"""Page-locked host buffers for results, recycled through a small pool.
+
+The feature matrix of a large graph is gigabytes; copying it into ordinary (pageable)
+numpy arrays goes through the CUDA driver's staging buffer at a few GB/s, while a
+page-locked destination is filled by DMA at PCIe rate.  Page-locking itself is slow, so
+blocks are pooled: a numpy array handed to the caller owns its block, and when the last
+reference to the array dies the block returns to the pool for the next call (a caller
+that keeps its result simply keeps the block).  ARCTE_CUDA_PINNED_RESULTS=0 switches to
+plain numpy arrays.
+"""
+import ctypes as C
+import os
+import threading
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+_POOL_LIMIT_BYTES = int(os.environ.get("ARCTE_CUDA_PINNED_POOL_GB", "48")) << 30
+_MIN_PINNED_BYTES = 1 << 20  # tiny results are not worth a pinned block
+
+_lock = threading.Lock()
+_free = []        # [(bytes, address)]
+_pooled_bytes = 0
+_threads = []
+
+
+def enabled():
+    return os.environ.get("ARCTE_CUDA_PINNED_RESULTS", "1") != "0"
+
+
+def _release(addr, nbytes):
+    global _pooled_bytes
+    with _lock:
+        if _pooled_bytes + nbytes <= _POOL_LIMIT_BYTES:
+            _free.append((nbytes, addr))
+            _pooled_bytes += nbytes
+            return
+    _lib.load().arcte_cuda_host_free(C.c_void_p(addr))
+
+
+def _acquire(nbytes):
+    global _pooled_bytes
+    with _lock:
+        best = None
+        for i, (b, a) in enumerate(_free):
+            if b >= nbytes and b <= nbytes + (nbytes >> 2) + 4096 and (best is None or b < _free[best][0]):
+                best = i
+        if best is not None:
+            b, a = _free.pop(best)
+            _pooled_bytes -= b
+            return a, b
+    return None, 0
+
+
+def _prepin(nbytes):
+    """Background: page-lock a block of this size for the NEXT call (pinning runs at a few
+    GB/s, slower than one pageable copy, so the call that first needs a size never waits)."""
+    global _pooled_bytes
+    with _lock:
+        if _pooled_bytes + nbytes > _POOL_LIMIT_BYTES:
+            return
+    p = C.c_void_p()
+    if _lib.load().arcte_cuda_host_alloc(C.byref(p), int(nbytes)) != 0:
+        return
+    _release(p.value, nbytes)
+
+
+def empty(count, dtype):
+    """Uninitialised 1-D array of `count` items: a pooled page-locked block when one of
+    the right size is free, else a plain numpy array (and a block is pinned in the
+    background for next time)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(count) * dtype.itemsize
+    if not enabled() or nbytes < _MIN_PINNED_BYTES:
+        return np.empty(int(count), dtype=dtype)
+    addr, block = _acquire(nbytes)
+    if addr is None:
+        t = threading.Thread(target=_prepin, args=(nbytes,), daemon=True)
+        t.start()
+        _threads.append(t)
+        return np.empty(int(count), dtype=dtype)
+    buf = (C.c_char * block).from_address(addr)
+    weakref.finalize(buf, _release, addr, block)
+    return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+
+def wait_idle():
+    """Block until every background pinning thread has finished (benchmarks, tests)."""
+    while _threads:
+        _threads.pop().join()
+
+
+def drain():
+    """Free every pooled block (tests)."""
+    global _pooled_bytes
+    with _lock:
+        blocks = list(_free)
+        _free.clear()
+        _pooled_bytes = 0
+    for _, a in blocks:
+        _lib.load().arcte_cuda_host_free(C.c_void_p(a))

@@ -1,0 +1,38 @@
+"""Multi-GPU paths (skipped unless the box exposes >= 2 GPUs): single-process sharding over
+several contexts with peer copies, and one-process-per-GPU sharding with an NCCL all-gather."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import EPS, GOLDEN_NAMES, RHO, assert_csr_identical, golden_features, load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    from reveal_graph_embedding_b200.engine import device_count
+    return device_count()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_in_process_multi_gpu_identical(name):
+    if n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from reveal_graph_embedding_b200.embedding.arcte.arcte import arcte
+    A, z = load_golden(name)
+    X = arcte(A, RHO, EPS, number_of_threads=n_gpus())
+    assert_csr_identical(X, golden_features(z, 0, A.shape[0]))
+
+
+def test_torchrun_nccl_identical():
+    g = n_gpus()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(g),
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "dist_check ok" in out.stdout

@@ -1,0 +1,26 @@
+"""torchrun target: every rank runs arcte() on a golden graph inside an NCCL process group
+and checks the full matrix bit-for-bit against the reference fixture.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/dist_check.py
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+from helpers import EPS, RHO, GOLDEN_NAMES, golden_features, load_golden, assert_csr_identical
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from reveal_graph_embedding_b200.embedding.arcte.arcte import arcte, arcte_with_lazy_pagerank
+for name in GOLDEN_NAMES:
+    A, z = load_golden(name)
+    X = arcte(A, RHO, EPS)
+    assert_csr_identical(X, golden_features(z, 0, A.shape[0]))
+    if "X2_data" in z:
+        assert_csr_identical(arcte_with_lazy_pagerank(A, RHO, EPS), golden_features(z, 2, A.shape[0]))
+dist.barrier()
+if dist.get_rank() == 0:
+    print("dist_check ok: world=%d, %d graphs" % (dist.get_world_size(), len(GOLDEN_NAMES)))
+dist.destroy_process_group()
