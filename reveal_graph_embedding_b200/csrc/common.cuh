@@ -207,4 +207,39 @@ template <typename F> __device__ double pairwise_sum(F at, int64_t off, int64_t 
     return ret;
 }
 
+// The same sum computed by a whole warp for long inputs, bit-identical to pairwise_sum():
+// the top (up to) five levels of numpy's split tree are unrolled over the lanes -- lane bits,
+// most significant first, choose left/right -- each lane sums its own subtree with the
+// sequential routine, and the partial sums are folded back up in tree order with shuffles.
+// All 32 lanes must call it with the same (off, n); every lane returns the total.
+template <typename F> __device__ double pairwise_sum_warp(F at, int64_t off, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t o = off, m = n;
+    int depth = 0;
+#pragma unroll
+    for (int lvl = 0; lvl < 5; ++lvl) {
+        if (m <= 128) break;
+        int64_t n2 = m / 2;
+        n2 -= n2 % 8;
+        if ((lane >> (4 - lvl)) & 1) {
+            o += n2;
+            m -= n2;
+        } else {
+            m = n2;
+        }
+        depth = lvl + 1;
+    }
+    // lanes sharing a node: identical top `depth` bits; the one with zero low bits computes it
+    const bool owner = (lane & ((1 << (5 - depth)) - 1)) == 0;
+    double val = owner ? pairwise_sum(at, o, m) : 0.0;
+#pragma unroll
+    for (int lvl = 4; lvl >= 0; --lvl) {
+        const double other = __shfl_xor_sync(kFull, val, 1 << (4 - lvl));
+        const bool left_holder = depth > lvl && (lane & ((1 << (5 - lvl)) - 1)) == 0;
+        if (left_holder) val = __dadd_rn(val, other);  // pairwise_sum(left) + pairwise_sum(right)
+    }
+    return __shfl_sync(kFull, val, 0);
+}
+
 }  // namespace arcte

@@ -19,6 +19,8 @@
 
 namespace arcte {
 
+constexpr int64_t kHeavyRow = 128;  // numpy's pairwise leaf size: longer sums are split over a warp
+
 // ---- K1a: out-degree, one thread per row ----------------------------------------------
 __global__ void __launch_bounds__(256)
 k_row_degree(int64_t n, const int64_t *__restrict__ indptr, const double *__restrict__ adj,
@@ -27,6 +29,7 @@ k_row_degree(int64_t n, const int64_t *__restrict__ indptr, const double *__rest
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t b = indptr[i], e = indptr[i + 1];
+    if (e - b - 1 > kHeavyRow) return;  // long rows: k_row_degree_heavy
     double sum = 0.0;
     if (e > b) {
         sum = adj[b];
@@ -37,6 +40,21 @@ k_row_degree(int64_t n, const int64_t *__restrict__ indptr, const double *__rest
     }
     if (sum == 0.0) sum = 1.0;  // transition.py:58
     d_out[i] = sum;
+}
+
+// Same for rows whose tail is longer than one pairwise leaf: one warp per row.
+__global__ void __launch_bounds__(256)
+k_row_degree_heavy(int64_t n, const int64_t *__restrict__ indptr, const double *__restrict__ adj,
+                   double *__restrict__ d_out)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int64_t b = indptr[i], e = indptr[i + 1];
+    if (e - b - 1 <= kHeavyRow) return;
+    auto at = [adj](int64_t j) { return adj[j]; };
+    double sum = __dadd_rn(adj[b], pairwise_sum_warp(at, b + 1, e - b - 1));
+    if (sum == 0.0) sum = 1.0;
+    if (lane_id() == 0) d_out[i] = sum;
 }
 
 // ---- K1b: binarised column counts + sort keys ------------------------------------------
@@ -119,7 +137,19 @@ k_seed_keys(int64_t n, const int32_t *__restrict__ colcnt, int32_t maxcnt, uint3
     ids[i] = (uint32_t)i;
 }
 
-// ---- K2b: epsilon-effective, one thread per seed --------------------------------------------
+// ---- K2b: epsilon-effective; one thread per seed, one warp per seed with > 128 neighbours ----
+__device__ __forceinline__ double eps_effective_finish(double epsilon, double ds, double mean, double dmin,
+                                                       double dmax)
+{
+    // arcte.py:35
+    double eff = __ddiv_rn(__dmul_rn(epsilon, log(__dadd_rn(1.0, ds))), log(__dadd_rn(1.0, mean)));
+    const double hi = __ddiv_rn(1.0, __dmul_rn(ds, dmin));  // arcte.py:39
+    const double lo = __ddiv_rn(1.0, __dmul_rn(ds, dmax));  // arcte.py:40
+    if (eff > hi) eff = hi;                                       // arcte.py:45-46
+    else if (eff < lo) eff = __ddiv_rn(__dadd_rn(lo, eff), 2.0);  // arcte.py:47-48
+    return eff;
+}
+
 __global__ void __launch_bounds__(128)
 k_eps_effective(int64_t n_seeds, const int32_t *__restrict__ seeds, double epsilon,
                 const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -130,7 +160,7 @@ k_eps_effective(int64_t n_seeds, const int32_t *__restrict__ seeds, double epsil
     const int32_t seed = seeds[k];
     const int64_t b = indptr[seed], e = indptr[seed + 1];
     const int64_t deg = e - b;
-    const double ds = d_out[seed];
+    if (deg > kHeavyRow) return;  // k_eps_effective_heavy
     auto at = [indices, d_out](int64_t j) { return d_out[indices[j]]; };
     const double mean = __ddiv_rn(pairwise_sum(at, b, deg), (double)deg);  // arcte.py:32
     double dmin = INFINITY, dmax = -INFINITY;
@@ -139,13 +169,34 @@ k_eps_effective(int64_t n_seeds, const int32_t *__restrict__ seeds, double epsil
         dmin = fmin(dmin, d);
         dmax = fmax(dmax, d);
     }
-    // arcte.py:35
-    double eff = __ddiv_rn(__dmul_rn(epsilon, log(__dadd_rn(1.0, ds))), log(__dadd_rn(1.0, mean)));
-    const double hi = __ddiv_rn(1.0, __dmul_rn(ds, dmin));  // arcte.py:39
-    const double lo = __ddiv_rn(1.0, __dmul_rn(ds, dmax));  // arcte.py:40
-    if (eff > hi) eff = hi;                                       // arcte.py:45-46
-    else if (eff < lo) eff = __ddiv_rn(__dadd_rn(lo, eff), 2.0);  // arcte.py:47-48
-    eps_out[k] = eff;
+    eps_out[k] = eps_effective_finish(epsilon, d_out[seed], mean, dmin, dmax);
+}
+
+__global__ void __launch_bounds__(256)
+k_eps_effective_heavy(int64_t n_seeds, const int32_t *__restrict__ seeds, double epsilon,
+                      const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                      const double *__restrict__ d_out, double *__restrict__ eps_out)
+{
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_seeds) return;
+    const int32_t seed = seeds[k];
+    const int64_t b = indptr[seed], e = indptr[seed + 1];
+    const int64_t deg = e - b;
+    if (deg <= kHeavyRow) return;
+    auto at = [indices, d_out](int64_t j) { return d_out[indices[j]]; };
+    const double mean = __ddiv_rn(pairwise_sum_warp(at, b, deg), (double)deg);  // arcte.py:32
+    double dmin = INFINITY, dmax = -INFINITY;
+    for (int64_t j = b + lane_id(); j < e; j += 32) {
+        const double d = d_out[indices[j]];
+        dmin = fmin(dmin, d);
+        dmax = fmax(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = fmin(dmin, __shfl_xor_sync(kFull, dmin, o));
+        dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+    }
+    if (lane_id() == 0) eps_out[k] = eps_effective_finish(epsilon, d_out[seed], mean, dmin, dmax);
 }
 
 static int bit_length(uint64_t v)
@@ -248,7 +299,9 @@ int build_transition(arcte_cuda_ctx *c)
 
     k_row_degree<<<grid_for(n, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->adj.as<double>(),
                                                    c->d_out.as<double>());
-    ++*launches;
+    k_row_degree_heavy<<<grid_for(n * 32, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->adj.as<double>(),
+                                                            c->d_out.as<double>());
+    *launches += 2;
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->colcnt.p, 0, sizeof(int32_t) * (size_t)n, st));
     if (nnz > 0) {
         k_col_count<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, c->indices.as<int32_t>(),
@@ -292,7 +345,10 @@ int compute_eps_effective(arcte_cuda_ctx *c, double epsilon, const int32_t *dev_
     k_eps_effective<<<grid_for(n_seeds, 128), 128, 0, c->stream>>>(
         n_seeds, dev_seeds, epsilon, c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
         c->d_out.as<double>(), dev_eps_out);
-    ++c->stats.launches;
+    k_eps_effective_heavy<<<grid_for(n_seeds * 32, 256), 256, 0, c->stream>>>(
+        n_seeds, dev_seeds, epsilon, c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
+        c->d_out.as<double>(), dev_eps_out);
+    c->stats.launches += 2;
     ARCTE_CUDA_TRY(cudaGetLastError());
     return ARCTE_OK;
 }

@@ -68,9 +68,17 @@ def allgather_segments(seg_seed, seg_count, seg_offset, members, group=None):
     return parts
 
 
-def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True):
-    """One rank's share of arcte(): walk this rank's seeds, all-gather, assemble.
-    Every rank returns the complete n x 2n CSR."""
+def result_on_all_ranks():
+    """ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: every rank assembles and returns the matrix.
+    Default: rank 0 only (the others return None) -- copying a multi-gigabyte matrix to
+    the host once per rank would dominate the call."""
+    import os
+    return os.environ.get("ARCTE_CUDA_RESULT_ON_ALL_RANKS", "0") == "1"
+
+
+def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_ranks=None):
+    """One rank's share of arcte(): walk this rank's seeds, all-gather the segments, and
+    (rank 0, or every rank when all_ranks) assemble and return the complete n x 2n CSR."""
     import torch
     import torch.distributed as dist
     from .engine import get_engine
@@ -81,6 +89,11 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True):
         eng.set_graph(A, canonical=True)
     eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
     parts, keep = gather_engine_segments(eng)
+    if all_ranks is None:
+        all_ranks = result_on_all_ranks()
+    if rank != 0 and not all_ranks:
+        del keep
+        return None
     eng.assemble(parts)
     del keep
     return eng.features()

@@ -12,8 +12,10 @@ each returning the scipy.sparse CSR the reference returns (n x 2n, float64, cano
 the workers n x n).  `number_of_threads` used to be the size of the multiprocessing pool
 (arcte.py:650); here it caps the number of GPUs the seeds are sharded over (None = all
 visible GPUs).  Inside a torch.distributed job (one process per GPU, e.g. torchrun) every
-rank calls the function with the same matrix, processes its round-robin shard of the
-seeds and receives the full matrix after an NCCL all-gather of the per-GPU segments.
+rank calls the function with the same matrix and processes its round-robin shard of the
+seeds; after an NCCL all-gather of the per-GPU segments rank 0 assembles and returns the
+full matrix (the other ranks return None; ARCTE_CUDA_RESULT_ON_ALL_RANKS=1 returns it
+everywhere).
 
 Differences from the reference, all on purpose:
   * no silent degradation: the reference prints and returns the base features when the

@@ -171,6 +171,7 @@ class Engine:
         indices = hostmem.empty(max(nnz, 1), np.int32)   # page-locked for large results
         data = hostmem.empty(max(nnz, 1), np.float64)
         check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        hostmem.start_pending()
         indices = indices[:nnz]
         data = data[:nnz]
         if max(2 * self.n, nnz) < 2 ** 31:

@@ -24,6 +24,7 @@ _lock = threading.Lock()
 _free = []        # [(bytes, address)]
 _pooled_bytes = 0
 _threads = []
+_pending = []
 
 
 def enabled():
@@ -76,14 +77,26 @@ def empty(count, dtype):
     if not enabled() or nbytes < _MIN_PINNED_BYTES:
         return np.empty(int(count), dtype=dtype)
     addr, block = _acquire(nbytes)
+    if os.environ.get("ARCTE_CUDA_DEBUG"):
+        import sys
+        print("[arcte] hostmem.empty(%d bytes): %s" % (nbytes, "pooled pinned block" if addr else "pageable"),
+              file=sys.stderr)
     if addr is None:
-        t = threading.Thread(target=_prepin, args=(nbytes,), daemon=True)
-        t.start()
-        _threads.append(t)
+        _pending.append(nbytes)  # pinned in the background once the caller's copy is done
         return np.empty(int(count), dtype=dtype)
     buf = (C.c_char * block).from_address(addr)
     weakref.finalize(buf, _release, addr, block)
     return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+
+def start_pending():
+    """Start page-locking blocks for the sizes that missed the pool (called after the
+    device-to-host copy that used the pageable fallback has finished, so the two do not
+    compete for the host's memory system)."""
+    while _pending:
+        t = threading.Thread(target=_prepin, args=(_pending.pop(),), daemon=True)
+        t.start()
+        _threads.append(t)
 
 
 def wait_idle():

@@ -27,12 +27,15 @@ def test_in_process_multi_gpu_identical(name):
     assert_csr_identical(X, golden_features(z, 0, A.shape[0]))
 
 
-def test_torchrun_nccl_identical():
+@pytest.mark.parametrize("everywhere", ["1", "0"])
+def test_torchrun_nccl_identical(everywhere):
+    """everywhere=1: every rank returns the matrix; 0 (default): rank 0 only, others None."""
     g = n_gpus()
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(g),
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dist_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, DIST_CHECK_ALL=everywhere))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "dist_check ok" in out.stdout
