@@ -221,13 +221,13 @@ def main():
     def step():
         """K1..K5 with the adjacency resident in HBM."""
         eng.build_transition()
-        eng.extract(RULE_ABSORBING, RHO, EPS, shard_rank=rank, shard_count=world)
         if world > 1:
-            parts, keep = ardist.gather_engine_segments(eng)
-            eng.assemble(parts)
-            del keep
-        else:
-            eng.assemble()
+            # walk own seed shard, all-gather segments, row-sharded assembly, concatenate on rank 0
+            out = ardist.extract_and_concatenate(eng, RULE_ABSORBING, RHO, EPS)
+            return None if out is None else out[3]
+        eng.extract(RULE_ABSORBING, RHO, EPS)
+        eng.assemble()
+        return eng.out_nnz
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # NVML start-up happens during the warm-up, not inside the timed steps
@@ -235,6 +235,7 @@ def main():
         step()
     launches0 = eng.stats()["launches"]
     step_ms, push_ms, alg_bytes, stage_ms = [], [], [], []
+    nnz_out = 0
     barrier()
     sampler.lines.clear()
     t_wall0 = time.perf_counter()
@@ -242,8 +243,10 @@ def main():
         eng.flush_l2()
         barrier()
         eng.timer_start()
-        step()
+        nnz_step = step()
         ms = eng.timer_stop()
+        if nnz_step is not None:
+            nnz_out = nnz_step
         st = eng.stats()
         step_ms.append(ms)
         push_ms.append(st["ms_push"])
@@ -254,7 +257,6 @@ def main():
     clocks = sampler.stop()
     st = eng.stats()
     launches = st["launches"] - launches0
-    nnz_out = eng.out_nnz
 
     total_ms = float(np.sum(step_ms))
     if world > 1:

@@ -159,8 +159,19 @@ int arcte_cuda_assemble(arcte_cuda_ctx *ctx, int n_parts, const int64_t *part_n_
                         const int64_t *part_n_members, const int32_t *const *dev_seg_seed, const int32_t *const *dev_seg_count,
                         const int64_t *const *dev_seg_offset, const int32_t *const *dev_members,
                         int64_t *nnz_out);
+/* Row-sharded form: assembles only rows [row_lo, row_hi) of the feature matrix (indptr has
+   row_hi-row_lo+1 entries starting at 0).  With one process per GPU every rank builds its own
+   row block from the all-gathered segments and the blocks are concatenated on one rank. */
+int arcte_cuda_assemble_rows(arcte_cuda_ctx *ctx, int n_parts, const int64_t *part_n_segments,
+                             const int64_t *part_n_members, const int32_t *const *dev_seg_seed,
+                             const int32_t *const *dev_seg_count, const int64_t *const *dev_seg_offset,
+                             const int32_t *const *dev_members, int64_t row_lo, int64_t row_hi,
+                             int64_t *nnz_out);
 int arcte_cuda_get_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *host_indices,
                             double *host_data);
+/* Device-resident views of the assembled block (for a collective library). */
+int arcte_cuda_features_device(arcte_cuda_ctx *ctx, const int64_t **dev_indptr, const int32_t **dev_indices,
+                               const double **dev_data, int64_t *n_rows, int64_t *nnz);
 
 /* -- page-locked host memory for results ------------------------------------- */
 /* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be

@@ -21,7 +21,7 @@ SYMBOLS = [
     "arcte_cuda_set_graph", "arcte_cuda_set_transition", "arcte_cuda_set_seeds", "arcte_cuda_build_transition", "arcte_cuda_get_transition",
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
     "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
-    "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_get_features",
+    "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features",
     "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
 
@@ -80,6 +80,9 @@ def load():
         L.arcte_cuda_segments_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.arcte_cuda_export_segments.argtypes = [vp, vp, vp, vp, vp]
         L.arcte_cuda_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+        L.arcte_cuda_assemble_rows.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, i64, C.POINTER(i64)]
+        L.arcte_cuda_features_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64),
+                                                 C.POINTER(i64)]
         L.arcte_cuda_get_features.argtypes = [vp, vp, vp, vp]
         L.arcte_cuda_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.arcte_cuda_host_free.argtypes = [vp]

@@ -53,7 +53,7 @@ struct SegPart {
     const int64_t *seg_offset;
     const int32_t *members;
 };
-int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts);
+int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t row_lo, int64_t row_hi);
 
 }  // namespace arcte
 
@@ -395,6 +395,16 @@ int arcte_cuda_assemble(arcte_cuda_ctx *c, int n_parts, const int64_t *part_n_se
                         const int32_t *const *dev_seg_count, const int64_t *const *dev_seg_offset,
                         const int32_t *const *dev_members, int64_t *nnz_out)
 {
+    if (!c) { set_error("null context"); return ARCTE_E_ARG; }
+    return arcte_cuda_assemble_rows(c, n_parts, part_n_segments, part_n_members, dev_seg_seed, dev_seg_count,
+                                    dev_seg_offset, dev_members, 0, c->n, nnz_out);
+}
+
+int arcte_cuda_assemble_rows(arcte_cuda_ctx *c, int n_parts, const int64_t *part_n_segments,
+                             const int64_t *part_n_members, const int32_t *const *dev_seg_seed,
+                             const int32_t *const *dev_seg_count, const int64_t *const *dev_seg_offset,
+                             const int32_t *const *dev_members, int64_t row_lo, int64_t row_hi, int64_t *nnz_out)
+{
     CHECK_CTX(c);
     std::vector<SegPart> parts;
     std::vector<DevBuf> stage;
@@ -421,7 +431,7 @@ int arcte_cuda_assemble(arcte_cuda_ctx *c, int n_parts, const int64_t *part_n_se
                                     (const int64_t *)d, (const int32_t *)e});
         }
     }
-    if (rc == ARCTE_OK) rc = assemble_parts(c, (int)parts.size(), parts.data());
+    if (rc == ARCTE_OK) rc = assemble_parts(c, (int)parts.size(), parts.data(), row_lo, row_hi);
     for (DevBuf &b : stage) dev_free(b);
     if (rc != ARCTE_OK) return rc;
     if (nnz_out) *nnz_out = c->out_nnz;
@@ -433,7 +443,7 @@ int arcte_cuda_get_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *ho
     CHECK_CTX(c);
     if (!c->have_features) { set_error("get_features: call assemble first"); return ARCTE_E_ARG; }
     if (host_indptr)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->out_indptr.p, sizeof(int64_t) * (size_t)(c->n + 1), cudaMemcpyDeviceToHost, c->stream));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->out_indptr.p, sizeof(int64_t) * (size_t)(c->out_rows + 1), cudaMemcpyDeviceToHost, c->stream));
     if (host_indices && c->out_nnz > 0)
         ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indices, c->out_indices.p, sizeof(int32_t) * (size_t)c->out_nnz, cudaMemcpyDeviceToHost, c->stream));
     if (host_data && c->out_nnz > 0)
@@ -482,6 +492,19 @@ int arcte_cuda_flush_l2(arcte_cuda_ctx *c)
     ARCTE_TRY(dev_reserve(c->l2_flush, bytes));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->l2_flush.p, 0x5a, bytes, c->stream));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ARCTE_OK;
+}
+
+int arcte_cuda_features_device(arcte_cuda_ctx *c, const int64_t **dev_indptr, const int32_t **dev_indices,
+                               const double **dev_data, int64_t *n_rows, int64_t *nnz)
+{
+    CHECK_CTX(c);
+    if (!c->have_features) { set_error("features_device: call assemble first"); return ARCTE_E_ARG; }
+    if (dev_indptr) *dev_indptr = c->out_indptr.as<int64_t>();
+    if (dev_indices) *dev_indices = c->out_indices.as<int32_t>();
+    if (dev_data) *dev_data = c->out_data.as<double>();
+    if (n_rows) *n_rows = c->out_rows;
+    if (nnz) *nnz = c->out_nnz;
     return ARCTE_OK;
 }
 

@@ -119,6 +119,7 @@ struct arcte_cuda_ctx {
     arcte::DevBuf out_indices;  // int32 [nnz_out]
     arcte::DevBuf out_data;     // double [nnz_out]
     int64_t out_nnz = 0;
+    int64_t out_rows = 0;       // rows of the assembled block (n unless row-sharded)
     bool have_features = false;
 
     // scratch shared by primitives

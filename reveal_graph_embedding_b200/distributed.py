@@ -76,27 +76,131 @@ def result_on_all_ranks():
     return os.environ.get("ARCTE_CUDA_RESULT_ON_ALL_RANKS", "0") == "1"
 
 
-def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_ranks=None):
-    """One rank's share of arcte(): walk this rank's seeds, all-gather the segments, and
-    (rank 0, or every rank when all_ranks) assemble and return the complete n x 2n CSR."""
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, address, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
+                                         "data": (int(address), False), "version": 2}
+
+
+def _view(address, count, typestr, device):
+    import torch
+    if count == 0:
+        dt = {"<i8": torch.int64, "<i4": torch.int32, "<f8": torch.float64}[typestr]
+        return torch.empty(0, dtype=dt, device=device)
+    return torch.as_tensor(_DeviceArray(address, count, typestr), device=device)
+
+
+def row_range(n, rank, world):
+    """Rows of the feature matrix rank `rank` assembles: equal contiguous blocks."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def extract_and_concatenate(eng, rule, rho_eff, epsilon):
+    """Steps 1-3 of the distributed call, everything staying in HBM.
+
+    1. walk this rank's round-robin shard of the seeds (K2b-K4);
+    2. ONE exchange of the walk results: NCCL all-gather of the member segments;
+    3. every rank assembles the row block [n*r/G, n*(r+1)/G) of the feature matrix (K5 on 1/G
+       of the entries); the blocks are concatenated on rank 0 with NCCL send/recv.
+    Returns (indptr, indices, data, nnz) device tensors on rank 0, None on the other ranks.
+    """
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from .engine import get_engine
     rank, world = dist.get_rank(), dist.get_world_size()
-    device = torch.cuda.current_device()
-    eng = engine or get_engine(device)
-    if upload:
-        eng.set_graph(A, canonical=True)
+    dev = torch.device("cuda", eng.device)
     eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
     parts, keep = gather_engine_segments(eng)
+    n = eng.n
+    lo, hi = row_range(n, rank, world)
+    eng.assemble(parts, row_lo=lo, row_hi=hi)
+    del keep
+    p_indptr, p_indices, p_data, n_rows, nnz = eng.features_device()
+    sizes = torch.tensor([nnz], dtype=torch.int64, device=dev)
+    all_nnz = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_nnz, sizes)
+    all_nnz = all_nnz.cpu().numpy()
+    offsets = np.concatenate([[0], np.cumsum(all_nnz)])
+    total = int(offsets[-1])
+    blk_indptr = _view(p_indptr, n_rows + 1, "<i8", dev)
+    blk_indices = _view(p_indices, nnz, "<i4", dev)
+    blk_data = _view(p_data, nnz, "<f8", dev)
+    torch.cuda.synchronize(dev)
+    if rank != 0:
+        ops = [dist.P2POp(dist.isend, blk_indptr, 0)]
+        if nnz > 0:
+            ops += [dist.P2POp(dist.isend, blk_indices, 0), dist.P2POp(dist.isend, blk_data, 0)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        torch.cuda.synchronize(dev)
+        return None
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    data = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+    tmp_ptr = []
+    ops = []
+    for r in range(1, world):
+        rlo, rhi = row_range(n, r, world)
+        t = torch.empty(rhi - rlo + 1, dtype=torch.int64, device=dev)
+        tmp_ptr.append((r, rlo, rhi, t))
+        ops.append(dist.P2POp(dist.irecv, t, r))
+        if all_nnz[r] > 0:
+            ops.append(dist.P2POp(dist.irecv, indices[int(offsets[r]):int(offsets[r + 1])], r))
+            ops.append(dist.P2POp(dist.irecv, data[int(offsets[r]):int(offsets[r + 1])], r))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    indptr[lo:hi + 1] = blk_indptr
+    indices[:nnz] = blk_indices
+    data[:nnz] = blk_data
+    for r in reqs:
+        r.wait()
+    for r, rlo, rhi, t in tmp_ptr:
+        indptr[rlo:rhi + 1] = t + int(offsets[r])
+    torch.cuda.synchronize(dev)
+    return indptr, indices, data, total
+
+
+def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_ranks=None):
+    """One rank's share of arcte() inside a torch.distributed job: see extract_and_concatenate.
+    Rank 0 copies the matrix to the host and returns it; the other ranks return None.  With
+    all_ranks (ARCTE_CUDA_RESULT_ON_ALL_RANKS=1) every rank assembles and returns the matrix."""
+    import numpy as np
+    import scipy.sparse as sparse
+    import torch
+    import torch.distributed as dist
+    from . import hostmem
+    from .engine import get_engine
+    rank, world = dist.get_rank(), dist.get_world_size()
+    eng = engine or get_engine(torch.cuda.current_device())
+    if upload:
+        eng.set_graph(A, canonical=True)
     if all_ranks is None:
         all_ranks = result_on_all_ranks()
-    if rank != 0 and not all_ranks:
+    if all_ranks:
+        eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
+        parts, keep = gather_engine_segments(eng)
+        eng.assemble(parts)
         del keep
+        return eng.features()
+    out = extract_and_concatenate(eng, rule, rho_eff, epsilon)
+    if out is None:
         return None
-    eng.assemble(parts)
-    del keep
-    return eng.features()
+    indptr, indices, data, total = out
+    n = eng.n
+    # device -> host into pooled page-locked buffers
+    h_indices = hostmem.empty(max(total, 1), np.int32)
+    h_data = hostmem.empty(max(total, 1), np.float64)
+    torch.from_numpy(h_indices).copy_(indices)
+    torch.from_numpy(h_data).copy_(data)
+    h_indptr = indptr.cpu().numpy()
+    hostmem.start_pending()
+    h_indices, h_data = h_indices[:total], h_data[:total]
+    if max(2 * n, total) < 2 ** 31:
+        h_indptr = h_indptr.astype(np.int32)
+    else:
+        h_indices = h_indices.astype(np.int64)
+    return sparse.csr_matrix((h_data, h_indices, h_indptr), shape=(n, 2 * n), copy=False)
 
 
 def gather_engine_segments(eng):

@@ -148,25 +148,48 @@ class Engine:
                                                  C.c_void_p(offset_ptr), C.c_void_p(members_ptr)))
 
     # -- a9-a10 ---------------------------------------------------------------------------------
-    def assemble(self, parts=None):
+    def assemble(self, parts=None, row_lo=0, row_hi=None):
         """parts: None (own segments) or a list of (n_segments, n_members, seed_ptr, count_ptr,
-        offset_ptr, members_ptr) with device addresses as ints."""
+        offset_ptr, members_ptr) with device addresses as ints.  row_lo/row_hi: assemble only
+        that row block of the feature matrix (default: all rows)."""
         nnz = C.c_int64()
+        row_hi = self.n if row_hi is None else int(row_hi)
         if not parts:
-            check(self._L.arcte_cuda_assemble(self._h, 0, None, None, None, None, None, None, C.byref(nnz)))
+            check(self._L.arcte_cuda_assemble_rows(self._h, 0, None, None, None, None, None, None, int(row_lo),
+                                                   row_hi, C.byref(nnz)))
         else:
             P = len(parts)
             ns = np.array([p[0] for p in parts], dtype=np.int64)
             nm = np.array([p[1] for p in parts], dtype=np.int64)
             cols = [np.array([p[i] for p in parts], dtype=np.uint64) for i in (2, 3, 4, 5)]
-            check(self._L.arcte_cuda_assemble(self._h, P, ptr(ns), ptr(nm), ptr(cols[0]), ptr(cols[1]),
-                                              ptr(cols[2]), ptr(cols[3]), C.byref(nnz)))
+            check(self._L.arcte_cuda_assemble_rows(self._h, P, ptr(ns), ptr(nm), ptr(cols[0]), ptr(cols[1]),
+                                                   ptr(cols[2]), ptr(cols[3]), int(row_lo), row_hi, C.byref(nnz)))
         self.out_nnz = nnz.value
+        self.out_rows = row_hi - int(row_lo)
         return nnz.value
+
+    def features_device(self):
+        """(indptr_ptr, indices_ptr, data_ptr, n_rows, nnz) of the assembled block on the device."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        r, z = C.c_int64(), C.c_int64()
+        check(self._L.arcte_cuda_features_device(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(r),
+                                                 C.byref(z)))
+        return a.value or 0, b.value or 0, c.value or 0, r.value, z.value
+
+    def features_block(self):
+        """Raw (indptr, indices, data) of the assembled row block (indptr starts at 0)."""
+        nnz, rows = self.out_nnz, getattr(self, "out_rows", self.n)
+        indptr = np.empty(rows + 1, dtype=np.int64)
+        indices = np.empty(max(nnz, 1), dtype=np.int32)
+        data = np.empty(max(nnz, 1), dtype=np.float64)
+        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        return indptr, indices[:nnz], data[:nnz]
 
     def features(self):
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
         nnz = self.out_nnz
+        if getattr(self, "out_rows", self.n) != self.n:
+            raise ArcteCudaError("features(): only a row block is assembled; use the distributed path")
         indptr = np.empty(self.n + 1, dtype=np.int64)
         indices = hostmem.empty(max(nnz, 1), np.int32)   # page-locked for large results
         data = hostmem.empty(max(nnz, 1), np.float64)
