@@ -122,6 +122,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
                       &c->out_indices, &c->out_data};
     for (DevBuf *b : bufs) dev_free(*b);
     for (DevBuf &b : c->scratch) dev_free(b);
+    for (DevBuf &b : c->peer_stage) dev_free(b);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->tm0);
@@ -385,6 +386,15 @@ static int localise(arcte_cuda_ctx *c, const void *p, size_t bytes, DevBuf &stag
         return ARCTE_E_ARG;
     }
     ARCTE_TRY(dev_reserve(stage, bytes));
+    {   // direct NVLink DMA needs peer access; "already enabled" / "not supported" are fine
+        // (without it the copy is staged through the host by the driver)
+        (void)cudaDeviceEnablePeerAccess(at.device, 0);
+        (void)cudaGetLastError();
+        (void)cudaSetDevice(at.device);
+        (void)cudaDeviceEnablePeerAccess(c->device, 0);
+        (void)cudaGetLastError();
+        (void)cudaSetDevice(c->device);
+    }
     ARCTE_CUDA_TRY(cudaMemcpyPeerAsync(stage.p, c->device, p, at.device, bytes, c->stream));
     *out = stage.p;
     return ARCTE_OK;
@@ -407,7 +417,6 @@ int arcte_cuda_assemble_rows(arcte_cuda_ctx *c, int n_parts, const int64_t *part
 {
     CHECK_CTX(c);
     std::vector<SegPart> parts;
-    std::vector<DevBuf> stage;
     int rc = ARCTE_OK;
     if (n_parts == 0) {
         if (!c->have_segments) { set_error("assemble: call extract first"); return ARCTE_E_ARG; }
@@ -419,7 +428,8 @@ int arcte_cuda_assemble_rows(arcte_cuda_ctx *c, int n_parts, const int64_t *part
             set_error("assemble: bad part arrays");
             return ARCTE_E_ARG;
         }
-        stage.resize((size_t)n_parts * 4);
+        if (n_parts > 16) { set_error("assemble: at most 16 parts"); return ARCTE_E_ARG; }
+        DevBuf *stage = c->peer_stage;
         for (int p = 0; p < n_parts && rc == ARCTE_OK; ++p) {
             const size_t S = (size_t)part_n_segments[p], M = (size_t)part_n_members[p];
             const void *a = nullptr, *b = nullptr, *d = nullptr, *e = nullptr;
@@ -432,7 +442,6 @@ int arcte_cuda_assemble_rows(arcte_cuda_ctx *c, int n_parts, const int64_t *part
         }
     }
     if (rc == ARCTE_OK) rc = assemble_parts(c, (int)parts.size(), parts.data(), row_lo, row_hi);
-    for (DevBuf &b : stage) dev_free(b);
     if (rc != ARCTE_OK) return rc;
     if (nnz_out) *nnz_out = c->out_nnz;
     return ARCTE_OK;

@@ -122,6 +122,10 @@ struct arcte_cuda_ctx {
     int64_t out_rows = 0;       // rows of the assembled block (n unless row-sharded)
     bool have_features = false;
 
+    // staging for segment parts that live on other GPUs (kept across calls: cudaMalloc/cudaFree
+    // serialise the whole process)
+    arcte::DevBuf peer_stage[64];
+
     // scratch shared by primitives
     arcte::DevBuf scratch[16];
 

@@ -29,7 +29,7 @@ import threading
 import numpy as np
 import scipy.sparse as sparse
 
-from ... import distributed
+from ... import distributed, hostmem
 from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, canonical_csr, device_count,
                        get_engine)
 
@@ -54,31 +54,81 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
         return eng.features()
 
     # single process, several GPUs: graph replicated, seeds dealt round-robin (arcte.py:651),
-    # one host thread per GPU (ctypes drops the GIL), segments joined on GPU 0 by peer copies.
+    # one host thread per GPU (ctypes drops the GIL).  After the walks every GPU pulls all
+    # segments over NVLink (peer copies), assembles its own block of rows and copies it
+    # straight into its slice of the result arrays -- one PCIe link per GPU.
     engines = [get_engine(d) for d in range(n_gpus)]
-    errors = []
+    n = A.shape[0]
 
-    def work(rank):
-        try:
-            e = engines[rank]
-            e.set_graph(A, canonical=True)
-            e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
-        except BaseException as exc:  # re-raised on the caller's thread
-            errors.append(exc)
+    def run_parallel(fn):
+        errors = []
 
-    threads = [threading.Thread(target=work, args=(r,)) for r in range(n_gpus)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
+        def call(rank):
+            try:
+                fn(rank)
+            except BaseException as exc:  # re-raised on the caller's thread
+                errors.append(exc)
+
+        threads = [threading.Thread(target=call, args=(r,)) for r in range(n_gpus)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def walk(rank):
+        e = engines[rank]
+        e.set_graph(A, canonical=True)
+        e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
+
+    import os
+    import time
+    dbg = os.environ.get("ARCTE_CUDA_DEBUG")
+    t0 = time.perf_counter()
+    run_parallel(walk)
+    t1 = time.perf_counter()
     parts = []
     for e in engines:
         a, b, c, d = e.segments_device()
         parts.append((e.n_segments, e.n_members, a, b, c, d))
-    engines[0].assemble(parts)
-    return engines[0].features()
+
+    def assemble(rank):
+        lo, hi = distributed.row_range(n, rank, n_gpus)
+        engines[rank].assemble(parts, row_lo=lo, row_hi=hi)
+
+    run_parallel(assemble)
+    t2 = time.perf_counter()
+    nnz = np.array([e.out_nnz for e in engines], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(nnz)])
+    total = int(offsets[-1])
+    indices = hostmem.empty(max(total, 1), np.int32)
+    data = hostmem.empty(max(total, 1), np.float64)
+    indptr = np.empty(n + 1, dtype=np.int64)
+    blocks = [None] * n_gpus
+
+    def fetch(rank):
+        lo, hi = distributed.row_range(n, rank, n_gpus)
+        ip = np.empty(hi - lo + 1, dtype=np.int64)
+        o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
+        engines[rank].features_into(ip, indices[o0:o1], data[o0:o1])
+        blocks[rank] = (lo, hi, ip)
+
+    run_parallel(fetch)
+    t3 = time.perf_counter()
+    if dbg:
+        import sys
+        print("[arcte] in-process %d GPUs: upload+walk %.1f ms, exchange+assemble %.1f ms, fetch %.1f ms"
+              % (n_gpus, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr)
+    hostmem.start_pending()
+    for rank, (lo, hi, ip) in enumerate(blocks):
+        indptr[lo:hi + 1] = ip + offsets[rank]
+    indices, data = indices[:total], data[:total]
+    if max(2 * n, total) < 2 ** 31:
+        indptr = indptr.astype(np.int32)
+    else:
+        indices = indices.astype(np.int64)
+    return sparse.csr_matrix((data, indices, indptr), shape=(n, 2 * n), copy=False)
 
 
 def arcte(adjacency_matrix, rho, epsilon, number_of_threads=None):

@@ -185,6 +185,16 @@ class Engine:
         check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
         return indptr, indices[:nnz], data[:nnz]
 
+    def features_into(self, indptr, indices, data):
+        """Copy the assembled block into caller-owned host arrays (slices of larger arrays are
+        fine): indptr int64[rows+1], indices int32[nnz], data float64[nnz]."""
+        rows = getattr(self, "out_rows", self.n)
+        assert indptr.dtype == np.int64 and indptr.size == rows + 1 and indptr.flags.c_contiguous
+        assert indices.dtype == np.int32 and indices.size == self.out_nnz and indices.flags.c_contiguous
+        assert data.dtype == np.float64 and data.size == self.out_nnz and data.flags.c_contiguous
+        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices) if self.out_nnz else None,
+                                              ptr(data) if self.out_nnz else None))
+
     def features(self):
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
         nnz = self.out_nnz
