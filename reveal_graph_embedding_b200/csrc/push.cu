@@ -72,12 +72,84 @@ __device__ __forceinline__ int warp_sum_i(int v)
 // State pairs are gathered at random over gigabytes: keep them out of L1 (L2-only loads and
 // stores) so L1 stays with what is re-read -- the FIFO ring, the touched list, node records,
 // CSR rows and the few spilled registers.
-#ifndef ARCTE_STATE_L1
+//
+// L2 eviction hints (experiment switches, see profiles/README.md):
+//   ARCTE_HINT_STATE  state pairs are loaded/stored with an L2 evict_first policy (they stream
+//                     through L2: the next use of a sector is milliseconds away);
+//   ARCTE_HINT_GRAPH  node records, column indices and transition weights are loaded with an
+//                     L2 evict_last policy (90 MB on the YouTube shape, re-read by every walk).
+// The policies are created once per thread (createpolicy is a register-only instruction).
+#ifndef ARCTE_HINT_STATE
+#define ARCTE_HINT_STATE 0
+#endif
+#ifndef ARCTE_HINT_GRAPH
+#define ARCTE_HINT_GRAPH 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#if ARCTE_HINT_STATE
+__device__ __forceinline__ double2 ld_state(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(l2_policy_evict_first()) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(double2 *p, double2 v)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;"
+                 :: "l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_evict_first()) : "memory");
+}
+#elif !defined(ARCTE_STATE_L1)
 __device__ __forceinline__ double2 ld_state(const double2 *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_state(double2 *p, double2 v) { __stcg(p, v); }
 #else
 __device__ __forceinline__ double2 ld_state(const double2 *p) { return *p; }
 __device__ __forceinline__ void st_state(double2 *p, double2 v) { *p = v; }
+#endif
+#if ARCTE_HINT_GRAPH
+__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p)
+{
+    NodeInfo v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                 : "=l"(*reinterpret_cast<unsigned long long *>(&v.d_in)),
+                   "=l"(*reinterpret_cast<unsigned long long *>(&v.begin))
+                 : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ double ld_info_din(const NodeInfo *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(&p->d_in), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ int ld_index(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ double ld_weight(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+#else
+__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p) { return *p; }
+__device__ __forceinline__ double ld_info_din(const NodeInfo *p) { return p->d_in; }
+__device__ __forceinline__ int ld_index(const int32_t *p) { return *p; }
+__device__ __forceinline__ double ld_weight(const double *p) { return *p; }
 #endif
 
 // Per-warp statistics live in shared memory (no registers held across the walk).
@@ -136,8 +208,8 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
             const unsigned j = base + k * 32 + lane;
             v[k] = -1;
             if (j < len) {
-                v[k] = idx[j];
-                p[k] = __dmul_rn(c, wgt[j]);
+                v[k] = ld_index(idx + j);
+                p[k] = __dmul_rn(c, ld_weight(wgt + j));
             }
         }
         // phase 2: their state pairs and in-degrees (independent gathers, all in flight)
@@ -147,7 +219,7 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
         for (int k = 0; k < kPushUnroll; ++k) {
             if (v[k] >= 0) {
                 o[k] = ld_state(&sr[v[k]]);
-                dv[k] = P.info[v[k]].d_in;
+                dv[k] = ld_info_din(&P.info[v[k]]);
             }
         }
         // phase 3: update and store (neighbours of one node are distinct: no ordering needed)
@@ -262,7 +334,7 @@ k_push_threshold(const PushParams P)
         // record one pop ahead was measured and dropped: the launch is bound by random DRAM
         // sectors, not by this dependent load -- profiles/README.md.)
         int u = seed;
-        NodeInfo iu = P.info[seed];
+        NodeInfo iu = ld_info(&P.info[seed]);
         bool first = true, ok = true;
         for (;;) {
             if (first || __ddiv_rn(su.y, iu.d_in) >= eps) {  // similarity.py:204
@@ -278,8 +350,8 @@ k_push_threshold(const PushParams P)
                 }
             }
             if (wk.head == wk.tail) break;
-u = queue[wk.head & qmask];
-            iu = P.info[u];
+            u = queue[wk.head & qmask];
+            iu = ld_info(&P.info[u]);
             wk.head += 1;
             su = ld_state(&sr[u]);
         }
@@ -336,7 +408,7 @@ u = queue[wk.head & qmask];
                 for (int k2 = 0; k2 < 2; ++k2)
                     if (v[k2] >= 0) {
                         o[k2] = ld_state(&sr[v[k2]]);
-                        d[k2] = P.info[v[k2]].d_in;
+                        d[k2] = ld_info_din(&P.info[v[k2]]);
                     }
 #pragma unroll
                 for (int k2 = 0; k2 < 2; ++k2)
@@ -360,7 +432,7 @@ u = queue[wk.head & qmask];
             for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
                 if (x[k2] >= 0) {
                     sx[k2] = ld_state(&sr[x[k2]]).x;
-                    dx[k2] = P.info[x[k2]].d_in;
+                    dx[k2] = ld_info_din(&P.info[x[k2]]);
                 }
             }
             __syncwarp();
