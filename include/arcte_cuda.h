@@ -173,6 +173,46 @@ int arcte_cuda_get_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *
 int arcte_cuda_features_device(arcte_cuda_ctx *ctx, const int64_t **dev_indptr, const int32_t **dev_indices,
                                const double **dev_data, int64_t *n_rows, int64_t *nnz);
 
+/* -- after the path: column normalisation and community weighting ---------- */
+/* These take and return HOST CSR arrays (canonical: sorted column indices) like the reference
+   functions take and return scipy matrices; n_cols < 2^31.  Bit-exact against numpy/sklearn
+   except for the logarithm inside normalize_columns / community_weighting (1-2 ulp). */
+
+/* normalize_columns, embedding/common.py:49-67: every column with more than one stored entry
+   is divided by sqrt(log(stored entries)).  Structure unchanged; host_data_out may alias
+   host_data_in. */
+int arcte_cuda_normalize_columns(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *host_indptr,
+                                 const int32_t *host_indices, const double *host_data_in, double *host_data_out);
+/* The same on the feature matrix the last arcte_cuda_assemble left on the device (all rows),
+   in place, before arcte_cuda_get_features: arcte() followed by normalize_columns()
+   (experiments/utility.py:207 + :66) without a host round trip. */
+int arcte_cuda_normalize_features(arcte_cuda_ctx *ctx);
+
+/* chi2_contingency_matrix, embedding/community_weighting.py:11-45.  X: n_rows x n_cols CSR
+   (pattern only).  Y: n_rows x n_classes label matrix as CSR with integer-valued data, i.e.
+   LabelBinarizer().fit_transform(y_train) (:19-21).  host_out: n_classes x n_cols, row-major. */
+int arcte_cuda_chi2_contingency(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *host_x_indptr,
+                                const int32_t *host_x_indices, int64_t n_classes, const int64_t *host_y_indptr,
+                                const int32_t *host_y_indices, const double *host_y_data, double *host_out);
+/* peak_snr_weight_aggregation, embedding/community_weighting.py:48-84.  The matrix is changed
+   in place like the reference does (nan -> 0, :49); host_weights_out has n_cols entries. */
+int arcte_cuda_peak_snr(arcte_cuda_ctx *ctx, int64_t n_classes, int64_t n_cols, double *host_cm_inout,
+                        double *host_weights_out);
+/* The two above back to back with the n_classes x n_cols matrix kept in HBM
+   (chi2_psnr_community_weighting, community_weighting.py:128-131, first two lines). */
+int arcte_cuda_chi2_psnr_weights(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *host_x_indptr,
+                                 const int32_t *host_x_indices, int64_t n_classes, const int64_t *host_y_indptr,
+                                 const int32_t *host_y_indices, const double *host_y_data, double *host_weights_out);
+/* community_weighting, embedding/community_weighting.py:87-125, for ONE matrix (the reference
+   treats X_train and X_test identically and independently): columns with more than one stored
+   entry are multiplied by 0 if weight == 0 else log(1 + weight); explicit zeros are dropped;
+   rows are l2-normalised with sklearn's left-to-right sum of squares.  Output buffers are
+   caller-allocated with room for the input's nnz; *out_nnz is the number of entries kept. */
+int arcte_cuda_community_weighting(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *host_indptr,
+                                   const int32_t *host_indices, const double *host_data,
+                                   const double *host_weights, int64_t *host_out_indptr, int32_t *host_out_indices,
+                                   double *host_out_data, int64_t *out_nnz);
+
 /* -- page-locked host memory for results ------------------------------------- */
 /* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be
    page-locked so the device-to-host copy runs at PCIe rate instead of through the

@@ -22,6 +22,8 @@ SYMBOLS = [
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
     "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
     "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features",
+    "arcte_cuda_normalize_columns", "arcte_cuda_normalize_features", "arcte_cuda_chi2_contingency", "arcte_cuda_peak_snr",
+    "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
     "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
 
@@ -84,6 +86,12 @@ def load():
         L.arcte_cuda_features_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64),
                                                  C.POINTER(i64)]
         L.arcte_cuda_get_features.argtypes = [vp, vp, vp, vp]
+        L.arcte_cuda_normalize_columns.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+        L.arcte_cuda_normalize_features.argtypes = [vp]
+        L.arcte_cuda_chi2_contingency.argtypes = [vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]
+        L.arcte_cuda_peak_snr.argtypes = [vp, i64, i64, vp, vp]
+        L.arcte_cuda_chi2_psnr_weights.argtypes = [vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]
+        L.arcte_cuda_community_weighting.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
         L.arcte_cuda_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.arcte_cuda_host_free.argtypes = [vp]
         L.arcte_cuda_timer_start.argtypes = [vp]

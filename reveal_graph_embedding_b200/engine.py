@@ -214,6 +214,87 @@ class Engine:
         X = sparse.csr_matrix((data, indices, indptr), shape=(self.n, 2 * self.n), copy=False)
         return X
 
+    # -- after the path: column normalisation / community weighting ----------------
+    @staticmethod
+    def _csr_arrays(X):
+        X = sparse.csr_matrix(X, dtype=np.float64)
+        if not X.has_sorted_indices:
+            X = X.copy()
+            X.sort_indices()
+        if X.shape[1] >= 2 ** 31:
+            raise ValueError("matrices with 2^31 or more columns are not supported")
+        return (X.shape, np.ascontiguousarray(X.indptr, dtype=np.int64),
+                np.ascontiguousarray(X.indices, dtype=np.int32), np.ascontiguousarray(X.data, dtype=np.float64))
+
+    def normalize_columns(self, features):
+        """embedding/common.py:49-67 on any scipy sparse matrix; returns a new CSR."""
+        shape, indptr, indices, data = self._csr_arrays(features)
+        out = np.empty_like(data)
+        check(self._L.arcte_cuda_normalize_columns(self._h, shape[0], shape[1], ptr(indptr),
+                                                   ptr(indices) if data.size else None,
+                                                   ptr(data) if data.size else None,
+                                                   ptr(out) if data.size else None))
+        idx_t = np.int32 if max(shape[1], data.size) < 2 ** 31 else np.int64
+        return sparse.csr_matrix((out, indices.astype(idx_t, copy=False), indptr.astype(idx_t)), shape=shape)
+
+    def normalize_features(self):
+        """normalize_columns on the assembled feature matrix resident on the device, in place."""
+        check(self._L.arcte_cuda_normalize_features(self._h))
+
+    def chi2_contingency(self, X_train, Y):
+        """embedding/community_weighting.py:11-45; Y = binarised label matrix (sparse)."""
+        shape, indptr, indices, _ = self._csr_arrays(X_train)
+        yshape, y_indptr, y_indices, y_data = self._csr_arrays(Y)
+        if yshape[0] != shape[0]:
+            raise ValueError("X_train and y_train have different numbers of rows")
+        out = np.zeros((yshape[1], shape[1]), dtype=np.float64)
+        check(self._L.arcte_cuda_chi2_contingency(self._h, shape[0], shape[1], ptr(indptr),
+                                                  ptr(indices) if indices.size else None, yshape[1], ptr(y_indptr),
+                                                  ptr(y_indices) if y_indices.size else None,
+                                                  ptr(y_data) if y_data.size else None, ptr(out)))
+        return out
+
+    def peak_snr(self, contingency_matrix):
+        """embedding/community_weighting.py:48-84; changes the matrix in place (nan -> 0)."""
+        cm = contingency_matrix
+        if not (isinstance(cm, np.ndarray) and cm.dtype == np.float64 and cm.ndim == 2 and cm.flags.c_contiguous):
+            raise ValueError("contingency matrix must be a C-contiguous 2-D float64 array")
+        w = np.zeros(cm.shape[1], dtype=np.float64)
+        check(self._L.arcte_cuda_peak_snr(self._h, cm.shape[0], cm.shape[1], ptr(cm), ptr(w)))
+        return w
+
+    def chi2_psnr_weights(self, X_train, Y):
+        """chi2_contingency followed by peak_snr with the K x F matrix kept in HBM."""
+        shape, indptr, indices, _ = self._csr_arrays(X_train)
+        yshape, y_indptr, y_indices, y_data = self._csr_arrays(Y)
+        if yshape[0] != shape[0]:
+            raise ValueError("X_train and y_train have different numbers of rows")
+        w = np.zeros(shape[1], dtype=np.float64)
+        check(self._L.arcte_cuda_chi2_psnr_weights(self._h, shape[0], shape[1], ptr(indptr),
+                                                   ptr(indices) if indices.size else None, yshape[1], ptr(y_indptr),
+                                                   ptr(y_indices) if y_indices.size else None,
+                                                   ptr(y_data) if y_data.size else None, ptr(w)))
+        return w
+
+    def community_weighting(self, X, community_weights):
+        """embedding/community_weighting.py:87-125 for one matrix; returns a new CSR."""
+        shape, indptr, indices, data = self._csr_arrays(X)
+        w = np.ascontiguousarray(community_weights, dtype=np.float64)
+        if w.size != shape[1]:
+            raise ValueError("one community weight per column is required")
+        out_indptr = np.zeros(shape[0] + 1, dtype=np.int64)
+        out_indices = np.empty(max(data.size, 1), dtype=np.int32)
+        out_data = np.empty(max(data.size, 1), dtype=np.float64)
+        nnz = C.c_int64()
+        check(self._L.arcte_cuda_community_weighting(self._h, shape[0], shape[1], ptr(indptr),
+                                                     ptr(indices) if data.size else None,
+                                                     ptr(data) if data.size else None, ptr(w) if w.size else None,
+                                                     ptr(out_indptr), ptr(out_indices), ptr(out_data), C.byref(nnz)))
+        k = nnz.value
+        idx_t = np.int32 if max(shape[1], k) < 2 ** 31 else np.int64
+        return sparse.csr_matrix((out_data[:k], out_indices[:k].astype(idx_t, copy=False), out_indptr.astype(idx_t)),
+                                 shape=shape)
+
     def timer_start(self):
         check(self._L.arcte_cuda_timer_start(self._h))
 

@@ -1,0 +1,110 @@
+"""Measure the steps after the ARCTE path on the features of a
+bench workload: normalize_columns (device-resident and host-to-host), chi2 + peak-SNR
+weights, community_weighting -- device time (CUDA events on the library's stream), end-to-end
+wall time, algorithmic bytes against the measured HBM peak, and the CPU oracle port beside it.
+
+    python tools/weighting_bench.py [youtube|flickr|baNxM] [n_classes] [train_rows]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import scipy.sparse as sparse
+
+from bench import EPS, RHO, make_graph
+from reveal_graph_embedding_b200.embedding.community_weighting import _label_matrix
+from reveal_graph_embedding_b200.engine import get_engine
+
+workload = sys.argv[1] if len(sys.argv) > 1 else "youtube"
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 47          # ASU-YouTube has 47 groups
+n_train = int(sys.argv[3]) if len(sys.argv) > 3 else 3170   # 10 % of its 31,703 labelled nodes
+peak = 6550.7
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+A = make_graph(workload)
+n = A.shape[0]
+eng = get_engine(0)
+eng.set_graph(A)
+eng.extract(0, RHO, EPS)
+eng.assemble()
+X = eng.features()
+nnz = X.nnz
+out = {"workload": workload, "n": n, "features_nnz": int(nnz), "n_cols": 2 * n, "classes": K, "train_rows": n_train,
+       "hbm_peak_gbs": peak}
+
+
+def timed(fn, reps=3):
+    best, res = None, None
+    for _ in range(reps):
+        eng.flush_l2()
+        eng.timer_start()
+        t = time.perf_counter()
+        res = fn()
+        wall = (time.perf_counter() - t) * 1e3
+        dev = eng.timer_stop()
+        if best is None or dev < best[0]:
+            best = (dev, wall)
+    return best[0], best[1], res
+
+
+# ---- normalize_columns, features resident in HBM (arcte -> normalize fused) ----
+def resident():
+    eng.assemble()          # restore un-normalised data (not timed separately: subtract below)
+    eng.normalize_features()
+dev_asm, _, _ = timed(lambda: eng.assemble())
+dev_both, _, _ = timed(resident)
+ms = dev_both - dev_asm
+alg = 24.0 * nnz + 12.0 * 2 * n    # histogram reads 4 B/entry; scaling reads 12, writes 8; per column 4+8
+out["normalize_resident"] = {"device_ms": round(ms, 3), "alg_bytes": alg, "alg_GBps": round(alg / ms / 1e6, 1),
+                             "frac_of_peak": round(alg / ms / 1e6 / peak, 4)}
+
+# ---- normalize_columns host -> host through the public call ----
+dev, wall, Xn = timed(lambda: eng.normalize_columns(X), reps=2)
+out["normalize_host_to_host"] = {"device_ms": round(dev, 2), "wall_ms": round(wall, 1),
+                                 "h2d_bytes": int(12 * nnz), "d2h_bytes": int(8 * nnz)}
+
+# ---- labels and folds (synthetic, seeded) ----
+rng = np.random.default_rng(47)
+Y = sparse.csr_matrix((rng.random((n, K)) < 2.0 / K).astype(np.int64))
+perm = rng.permutation(n)
+train, test = np.sort(perm[:n_train]), np.sort(perm[n_train:])
+t = time.perf_counter()
+X_train, X_test, y_train = Xn[train, :], Xn[test, :], Y[train, :]
+out["host_row_slicing_ms"] = round((time.perf_counter() - t) * 1e3, 1)
+Yb = _label_matrix(y_train)
+
+# ---- chi2 + peak SNR, K x F matrix kept in HBM ----
+dev, wall, w = timed(lambda: eng.chi2_psnr_weights(X_train, Yb))
+F = 2 * n
+alg = 8.0 * K * F * 5 + 12.0 * X_train.nnz  # zero, accumulate/finish RMW, 2 variance reads, weights read
+out["chi2_psnr_weights"] = {"device_ms": round(dev, 3), "wall_ms": round(wall, 1), "train_nnz": int(X_train.nnz),
+                            "alg_bytes": alg, "alg_GBps": round(alg / dev / 1e6, 1),
+                            "frac_of_peak": round(alg / dev / 1e6 / peak, 4)}
+
+# ---- community_weighting on the test block (the large one) ----
+dev, wall, Xw = timed(lambda: eng.community_weighting(X_test, w), reps=2)
+out["community_weighting_test_block"] = {"device_ms": round(dev, 2), "wall_ms": round(wall, 1), "nnz_in": int(X_test.nnz),
+                                         "nnz_out": int(Xw.nnz)}
+
+# ---- the CPU oracle port beside it (single thread, same inputs) ----
+if "--no-cpu" not in sys.argv:
+    from oracle import weighting_oracle as wo
+    t = time.perf_counter(); On = wo.normalize_columns(X); t_norm = time.perf_counter() - t
+    t = time.perf_counter(); cm = wo.chi2_contingency_matrix(X_train, y_train); wo_w = wo.peak_snr_weight_aggregation(cm)
+    t_chi = time.perf_counter() - t
+    t = time.perf_counter(); Ow = wo._weight_one(X_test, wo_w); t_w = time.perf_counter() - t
+    out["cpu_oracle_port_1_thread_ms"] = {"normalize_columns": round(t_norm * 1e3, 1), "chi2_psnr": round(t_chi * 1e3, 1),
+                                          "community_weighting_test_block": round(t_w * 1e3, 1)}
+    out["parity_vs_oracle"] = {
+        "normalize_max_ulp": int(np.abs(On.data.view(np.int64) - Xn.data.view(np.int64)).max()),
+        "weights_bit_exact": bool(np.array_equal(w, wo_w)),
+        "weighted_structure_equal": bool(np.array_equal(Ow.indices, Xw.indices) and np.array_equal(Ow.indptr, Xw.indptr)),
+        "weighted_max_ulp": int(np.abs(Ow.data.view(np.int64) - Xw.data.view(np.int64)).max())}
+print(json.dumps(out))
