@@ -213,6 +213,25 @@ int arcte_cuda_community_weighting(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t 
                                    const double *host_weights, int64_t *host_out_indptr, int32_t *host_out_indices,
                                    double *host_out_data, int64_t *out_nnz);
 
+/* -- text I/O of the console script (host only) ------------------------ */
+/* read_adjacency_matrix, datautil/datarw.py:54-120: parses `src<sep>dst<sep>weight` rows
+   ('#' comments) with all host threads (n_threads <= 0: every hardware thread), renumbers the
+   node ids 0..n-1 in first-seen order (source before target) and, if `undirected`, appends the
+   reciprocal entry after each edge (self loops once).  The entries come back in file order as
+   COO triplets; node_ids[i] is the original id of node i (the reference's node_to_id). */
+typedef struct arcte_cuda_edge_list arcte_cuda_edge_list;
+int arcte_cuda_io_read_edge_list(const char *path, const char *separator, int undirected, int n_threads,
+                                 arcte_cuda_edge_list **out, int64_t *n_nodes, int64_t *n_entries);
+int arcte_cuda_io_edge_list_copy(const arcte_cuda_edge_list *el, int64_t *row, int64_t *col, double *data,
+                                 int64_t *node_ids);
+void arcte_cuda_io_edge_list_free(arcte_cuda_edge_list *el);
+/* write_features, datautil/datarw.py:123-143: one `node_id<sep>column<sep>int(value)` line per
+   stored entry of the CSR, row-major, formatted by all host threads and written with pwrite at
+   precomputed offsets. */
+int arcte_cuda_io_write_features(const char *path, const char *separator, int64_t n_rows, const int64_t *indptr,
+                                 const int32_t *indices, const double *data, const int64_t *node_ids,
+                                 int n_threads, int64_t *bytes_written);
+
 /* -- page-locked host memory for results ------------------------------------- */
 /* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be
    page-locked so the device-to-host copy runs at PCIe rate instead of through the

@@ -24,6 +24,7 @@ SYMBOLS = [
     "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features",
     "arcte_cuda_normalize_columns", "arcte_cuda_normalize_features", "arcte_cuda_chi2_contingency", "arcte_cuda_peak_snr",
     "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
+    "arcte_cuda_io_read_edge_list", "arcte_cuda_io_edge_list_copy", "arcte_cuda_io_edge_list_free", "arcte_cuda_io_write_features",
     "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
 
@@ -92,6 +93,12 @@ def load():
         L.arcte_cuda_peak_snr.argtypes = [vp, i64, i64, vp, vp]
         L.arcte_cuda_chi2_psnr_weights.argtypes = [vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]
         L.arcte_cuda_community_weighting.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+        L.arcte_cuda_io_read_edge_list.argtypes = [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(vp), C.POINTER(i64),
+                                                   C.POINTER(i64)]
+        L.arcte_cuda_io_edge_list_copy.argtypes = [vp, vp, vp, vp, vp]
+        L.arcte_cuda_io_edge_list_free.argtypes = [vp]
+        L.arcte_cuda_io_edge_list_free.restype = None
+        L.arcte_cuda_io_write_features.argtypes = [C.c_char_p, C.c_char_p, i64, vp, vp, vp, vp, i32, C.POINTER(i64)]
         L.arcte_cuda_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.arcte_cuda_host_free.argtypes = [vp]
         L.arcte_cuda_timer_start.argtypes = [vp]
@@ -99,7 +106,7 @@ def load():
         L.arcte_cuda_flush_l2.argtypes = [vp]
         L.arcte_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
         for s in SYMBOLS:
-            if s not in ("arcte_cuda_last_error", "arcte_cuda_destroy"):
+            if s not in ("arcte_cuda_last_error", "arcte_cuda_destroy", "arcte_cuda_io_edge_list_free"):
                 getattr(L, s).restype = C.c_int
         _lib = L
         return _lib

@@ -229,11 +229,12 @@ class Engine:
     def normalize_columns(self, features):
         """embedding/common.py:49-67 on any scipy sparse matrix; returns a new CSR."""
         shape, indptr, indices, data = self._csr_arrays(features)
-        out = np.empty_like(data)
+        out = hostmem.empty(data.size, np.float64)   # page-locked for large results
         check(self._L.arcte_cuda_normalize_columns(self._h, shape[0], shape[1], ptr(indptr),
                                                    ptr(indices) if data.size else None,
                                                    ptr(data) if data.size else None,
                                                    ptr(out) if data.size else None))
+        hostmem.start_pending()
         idx_t = np.int32 if max(shape[1], data.size) < 2 ** 31 else np.int64
         return sparse.csr_matrix((out, indices.astype(idx_t, copy=False), indptr.astype(idx_t)), shape=shape)
 
@@ -283,13 +284,14 @@ class Engine:
         if w.size != shape[1]:
             raise ValueError("one community weight per column is required")
         out_indptr = np.zeros(shape[0] + 1, dtype=np.int64)
-        out_indices = np.empty(max(data.size, 1), dtype=np.int32)
-        out_data = np.empty(max(data.size, 1), dtype=np.float64)
+        out_indices = hostmem.empty(max(data.size, 1), np.int32)
+        out_data = hostmem.empty(max(data.size, 1), np.float64)
         nnz = C.c_int64()
         check(self._L.arcte_cuda_community_weighting(self._h, shape[0], shape[1], ptr(indptr),
                                                      ptr(indices) if data.size else None,
                                                      ptr(data) if data.size else None, ptr(w) if w.size else None,
                                                      ptr(out_indptr), ptr(out_indices), ptr(out_data), C.byref(nnz)))
+        hostmem.start_pending()
         k = nnz.value
         idx_t = np.int32 if max(shape[1], k) < 2 ** 31 else np.int64
         return sparse.csr_matrix((out_data[:k], out_indices[:k].astype(idx_t, copy=False), out_indptr.astype(idx_t)),

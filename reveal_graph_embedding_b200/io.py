@@ -1,50 +1,104 @@
 """Edge-list reader and feature writer with the reference's wire formats
-(reveal_graph_embedding/datautil/datarw.py:54-143), vectorised with numpy."""
+(reveal_graph_embedding/datautil/datarw.py:54-143), same names and arguments.
+
+The reference parses the edge list line by line and writes the features entry by entry in
+Python; around a one-second GPU extraction that is the whole wall time of the `arcte`
+console script.  Both run in the native library (csrc/textio.cu, all host threads) through
+the C ABI: arcte_cuda_io_read_edge_list / arcte_cuda_io_write_features.
+"""
+import ctypes as C
+
 import numpy as np
 import scipy.sparse as spsp
 
+from . import _lib
+from ._lib import check, ptr
 
-def read_adjacency_matrix(file_path, separator, undirected):
+
+class NodeIds(dict):
+    """node_to_id of datarw.py:110-111 (anonymised index -> original node id), kept as one
+    int64 array so a million-node mapping costs no Python objects until it is looked at."""
+
+    def __init__(self, ids):
+        super().__init__()
+        self.array = np.ascontiguousarray(ids, dtype=np.int64)
+        self._filled = False
+
+    def _fill(self):
+        if not self._filled:
+            self._filled = True
+            super().update(zip(range(self.array.size), self.array.tolist()))
+
+    def __getitem__(self, k):
+        return int(self.array[k])
+
+    def __len__(self):
+        return int(self.array.size)
+
+    def __contains__(self, k):
+        return isinstance(k, (int, np.integer)) and 0 <= k < self.array.size
+
+    def __iter__(self):
+        return iter(range(self.array.size))
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def __eq__(self, other):
+        self._fill()
+        return dict.__eq__(self, other)
+
+    def __repr__(self):
+        self._fill()
+        return dict.__repr__(self)
+
+
+def read_adjacency_matrix(file_path, separator, undirected, number_of_threads=0):
     """datarw.py:54-120: `src<sep>dst<sep>weight` rows, '#' comments; node ids are remapped
     to 0..n-1 in first-seen order (source before target).  Returns (COO matrix, node_to_id)."""
-    src, dst, wgt = [], [], []
-    with open(file_path, "r") as f:
-        for line in f:
-            line = line.strip()
-            if not line or line[0] == "#":
-                continue
-            parts = line.split(separator)
-            src.append(int(parts[0]))
-            dst.append(int(parts[1]))
-            wgt.append(float(parts[2]))
-    src = np.asarray(src, dtype=np.int64)
-    dst = np.asarray(dst, dtype=np.int64)
-    wgt = np.asarray(wgt, dtype=np.float64)
-    # first-seen order over the interleaved stream s0, t0, s1, t1, ...
-    inter = np.empty(2 * src.size, dtype=np.int64)
-    inter[0::2] = src
-    inter[1::2] = dst
-    uniq, first = np.unique(inter, return_index=True)
-    order = np.argsort(first, kind="stable")
-    rank = np.empty(uniq.size, dtype=np.int64)
-    rank[order] = np.arange(uniq.size)
-    row = rank[np.searchsorted(uniq, src)]
-    col = rank[np.searchsorted(uniq, dst)]
-    node_to_id = {int(i): int(uniq[order[i]]) for i in range(uniq.size)}
-    if undirected:
-        m = row != col
-        row, col, wgt = (np.concatenate([row, col[m]]), np.concatenate([col, row[m]]),
-                         np.concatenate([wgt, wgt[m]]))
-    n = uniq.size
-    return spsp.coo_matrix((wgt, (row, col)), shape=(n, n)), node_to_id
+    L = _lib.load()
+    h, n, m = C.c_void_p(), C.c_int64(), C.c_int64()
+    check(L.arcte_cuda_io_read_edge_list(str(file_path).encode(), str(separator).encode(), int(bool(undirected)),
+                                         int(number_of_threads), C.byref(h), C.byref(n), C.byref(m)))
+    try:
+        row = np.empty(max(m.value, 1), dtype=np.int64)
+        col = np.empty(max(m.value, 1), dtype=np.int64)
+        data = np.empty(max(m.value, 1), dtype=np.float64)
+        ids = np.empty(max(n.value, 1), dtype=np.int64)
+        check(L.arcte_cuda_io_edge_list_copy(h, ptr(row), ptr(col), ptr(data), ptr(ids)))
+    finally:
+        L.arcte_cuda_io_edge_list_free(h)
+    k, nn = m.value, n.value
+    adjacency_matrix = spsp.coo_matrix((data[:k], (row[:k], col[:k])), shape=(nn, nn))
+    return adjacency_matrix, NodeIds(ids[:nn])
 
 
-def write_features(file_path, features, separator, node_to_id):
+def write_features(file_path, features, separator, node_to_id, number_of_threads=0):
     """datarw.py:123-143: one `node_id<sep>community_id<sep>int(value)` row per stored entry,
-    in COO order of the CSR."""
-    features = spsp.coo_matrix(features)
-    ids = np.array([node_to_id[i] for i in range(features.shape[0])], dtype=np.int64)
-    node = ids[features.row]
-    with open(file_path, "w") as f:
-        for a, b, c in zip(node.tolist(), features.col.tolist(), features.data.astype(np.int64).tolist()):
-            f.write("%d%s%d%s%d\n" % (a, separator, b, separator, c))
+    in the COO order of the CSR (row-major).  Returns the number of bytes written."""
+    X = spsp.csr_matrix(features)
+    if isinstance(node_to_id, NodeIds):
+        ids = node_to_id.array
+    else:
+        ids = np.array([node_to_id[i] for i in range(X.shape[0])], dtype=np.int64)
+    if ids.size != X.shape[0]:
+        raise ValueError("node_to_id must map every row of the feature matrix")
+    indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+    data = np.ascontiguousarray(X.data, dtype=np.float64)
+    nbytes = C.c_int64()
+    check(_lib.load().arcte_cuda_io_write_features(str(file_path).encode(), str(separator).encode(), X.shape[0],
+                                                   ptr(indptr), ptr(indices) if indices.size else None,
+                                                   ptr(data) if data.size else None,
+                                                   ptr(np.ascontiguousarray(ids)) if ids.size else None,
+                                                   int(number_of_threads), C.byref(nbytes)))
+    return nbytes.value

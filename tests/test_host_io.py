@@ -57,3 +57,103 @@ def test_cli_end_to_end_matches_reference_file(tmp_path):
     out = tmp_path / "features.tsv"
     main(["-i", os.path.join(GOLDEN_DIR, "cli_edges.tsv"), "-o", str(out), "-nt", "1"])
     assert out.read_text() == open(os.path.join(GOLDEN_DIR, "cli_features.tsv")).read()
+
+
+# ---- native parser / formatter (csrc/textio.cu) against the reference's Python semantics ----
+def _python_read(path, separator, undirected):
+    """datarw.py:54-120 restated with plain Python (line.strip().split(separator), int, float)."""
+    id_to_node, row, col, data = {}, [], [], []
+    for line in open(path):
+        f = line.strip().split(separator)
+        if not f[0] or f[0][0] == "#":
+            continue
+        s = id_to_node.setdefault(int(f[0]), len(id_to_node))
+        t = id_to_node.setdefault(int(f[1]), len(id_to_node))
+        w = float(f[2])
+        row.append(s); col.append(t); data.append(w)
+        if undirected and s != t:
+            row.append(t); col.append(s); data.append(w)
+    ids = [None] * len(id_to_node)
+    for k, v in id_to_node.items():
+        ids[v] = k
+    return np.array(row), np.array(col), np.array(data), ids
+
+
+@pytest.mark.parametrize("separator,undirected,threads", [("\t", False, 0), (",", True, 3), ("::", False, 7),
+                                                          (" ", True, 1)])
+def test_native_reader_equals_python_semantics(tmp_path, separator, undirected, threads):
+    from reveal_graph_embedding_b200.io import read_adjacency_matrix
+    rng = np.random.default_rng(len(separator) * 7 + threads)
+    ids = np.unique(rng.integers(-50, 10 ** 12, size=8000))[:4000]
+    lines = ["# header", "#x%sy%sz" % (separator, separator)]
+    fmts = ["%d", "%.3f", "%.17g", "%e"]
+    for i in range(60000):                       # ~1.5 MB: many 64 KB parser chunks
+        a, b = rng.choice(ids, size=2)
+        w = fmts[i % 4] % (rng.uniform(0.01, 50.0) if i % 4 else rng.integers(1, 9))
+        extra = (separator + "ignored") if i % 97 == 0 else ""
+        pad = "  " if i % 31 == 0 and separator != " " else ""
+        lines.append("%s%d%s%d%s%s%s%s" % (pad, a, separator, b, separator, w, extra, pad))
+        if i % 5000 == 0:
+            lines.append("")                     # blank line (skipped)
+    p = tmp_path / "edges.txt"
+    p.write_text("\n".join(lines))               # no trailing newline on the last row
+    A, node_to_id = read_adjacency_matrix(str(p), separator, undirected, number_of_threads=threads)
+    row, col, data, want_ids = _python_read(str(p), separator, undirected)
+    assert np.array_equal(A.row, row) and np.array_equal(A.col, col) and np.array_equal(A.data, data)
+    assert A.shape == (len(want_ids), len(want_ids))
+    assert [node_to_id[i] for i in range(len(want_ids))] == want_ids
+    assert dict(node_to_id.items()) == dict(enumerate(want_ids))
+
+
+def test_native_reader_reports_the_bad_line(tmp_path):
+    from reveal_graph_embedding_b200._lib import ArcteCudaError
+    from reveal_graph_embedding_b200.io import read_adjacency_matrix
+    p = tmp_path / "bad.tsv"
+    p.write_text("1\t2\t1.0\n# fine\n3\tfour\t1.0\n")
+    with pytest.raises(ArcteCudaError, match="line 3"):
+        read_adjacency_matrix(str(p), "\t", False)
+    with pytest.raises(ArcteCudaError, match="cannot open"):
+        read_adjacency_matrix(str(tmp_path / "missing.tsv"), "\t", False)
+    q = tmp_path / "short.tsv"
+    q.write_text("1\t2\n")
+    with pytest.raises(ArcteCudaError, match="line 1"):
+        read_adjacency_matrix(str(q), "\t", False)
+
+
+def test_native_reader_empty_file(tmp_path):
+    from reveal_graph_embedding_b200.io import read_adjacency_matrix
+    p = tmp_path / "empty.tsv"
+    p.write_text("# nothing\n")
+    A, ids = read_adjacency_matrix(str(p), "\t", False)
+    assert A.shape == (0, 0) and A.nnz == 0 and len(ids) == 0
+
+
+@pytest.mark.parametrize("threads", [0, 1, 5])
+def test_native_writer_equals_python_semantics(tmp_path, threads):
+    from reveal_graph_embedding_b200.io import write_features
+    rng = np.random.default_rng(threads)
+    n = 3000
+    X = sparse.random(n, 2 * n, density=0.02, random_state=rng, format="csr",
+                      data_rvs=lambda k: rng.choice([1.0, 2.0, 0.0, -3.7, 1e6 + 0.9, 123456789012.0], size=k))
+    X = sparse.lil_matrix(X)
+    X[17, :] = 0                                  # an empty row in the middle
+    X = sparse.csr_matrix(X)
+    X.data[::11] = 0.0                            # explicit zeros are written too
+    ids = np.unique(rng.integers(-10 ** 6, 10 ** 15, size=2 * n))[:n]
+    rng.shuffle(ids)
+    node_to_id = {i: int(v) for i, v in enumerate(ids)}
+    out = tmp_path / "f.txt"
+    nbytes = write_features(str(out), X, ";;", node_to_id, number_of_threads=threads)
+    coo = sparse.coo_matrix(X)                    # datarw.py:127-143
+    want = "".join(str(node_to_id[r]) + ";;" + str(c) + ";;" + str(int(v)) + "\n"
+                   for r, c, v in zip(coo.row.tolist(), coo.col.tolist(), coo.data.tolist()))
+    got = out.read_text()
+    assert got == want and nbytes == len(want)
+
+
+def test_native_writer_rejects_non_finite(tmp_path):
+    from reveal_graph_embedding_b200._lib import ArcteCudaError
+    from reveal_graph_embedding_b200.io import write_features
+    X = sparse.csr_matrix(np.array([[1.0, np.nan], [0.0, 2.0]]))
+    with pytest.raises(ArcteCudaError, match="not a finite"):
+        write_features(str(tmp_path / "f.txt"), X, "\t", {0: 5, 1: 6})
