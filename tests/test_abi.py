@@ -73,6 +73,7 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "arcte_oracle" not in text and "liboracle" not in text, os.path.join(dirpath, f)
+                assert "weighting_oracle" not in text, os.path.join(dirpath, f)
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
 
 
