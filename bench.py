@@ -326,9 +326,18 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    # DRAM bytes of one launch of the same kernel on the same workload from the committed
+    # `ncu --set full` capture (per launch, like `achieved`); null for any other configuration.
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_push_youtube_traffic.json")))
+        if args.workload == cap["workload"] and world == cap["n_gpus"]:
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
     achieved = alg_job / (push_ms_job / 1e3) / 1e9 / world  # per GPU: each GPU ran alg_job/world bytes
     roofline = {"bound": "hbm", "kernel": "k_push_threshold<absorbing>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_job / world, "kernel_ms": push_ms_job,
                 "pushes": st["pushes"], "edge_touches": st["edge_touches"], "support": st["support"],
                 "note": "achieved = SURVEY 8(d) algorithmic bytes of this GPU's seeds / push-kernel time "

@@ -247,4 +247,41 @@ template <typename F> __device__ double pairwise_sum_warp(F at, int64_t off, int
     return __shfl_sync(kFull, val, 0);
 }
 
+// The same sum computed by a whole CTA of 1024 threads (10 tree levels over the thread index,
+// most significant bit first), bit-identical to pairwise_sum().  `red` is 1024 doubles of shared
+// memory.  Every thread must call it with the same (off, n); every thread returns the total.
+template <typename F> __device__ double pairwise_sum_block1024(F at, int64_t off, int64_t n, double *red)
+{
+    const int t = threadIdx.x;
+    int64_t o = off, m = n;
+    int depth = 0;
+#pragma unroll
+    for (int lvl = 0; lvl < 10; ++lvl) {
+        if (m <= 128) break;
+        int64_t n2 = m / 2;
+        n2 -= n2 % 8;
+        if ((t >> (9 - lvl)) & 1) {
+            o += n2;
+            m -= n2;
+        } else {
+            m = n2;
+        }
+        depth = lvl + 1;
+    }
+    const bool owner = (t & ((1 << (10 - depth)) - 1)) == 0;
+    double val = owner ? pairwise_sum(at, o, m) : 0.0;
+    for (int lvl = 9; lvl >= 0; --lvl) {
+        red[t] = val;
+        __syncthreads();
+        const bool left_holder = depth > lvl && (t & ((1 << (10 - lvl)) - 1)) == 0;
+        if (left_holder) val = __dadd_rn(val, red[t ^ (1 << (9 - lvl))]);  // left + right
+        __syncthreads();
+    }
+    if (t == 0) red[0] = val;
+    __syncthreads();
+    const double total = red[0];
+    __syncthreads();
+    return total;
+}
+
 }  // namespace arcte

@@ -174,20 +174,24 @@ __global__ void k_nan_to_zero(int64_t n, double *__restrict__ a)
 }
 
 // np.var of every class row (community_weighting.py:52-54): numpy's pairwise tree twice --
-// mean = sum/F, then sum((a-mean)^2)/F.  One warp per class.
-__global__ void k_row_variance(int64_t K, int64_t F, const double *__restrict__ cm, double *__restrict__ variance)
+// mean = sum/F, then sum((a-mean)^2)/F.  One CTA of 1024 threads per class: the top ten levels
+// of numpy's split tree are spread over the threads, every thread streams its own contiguous
+// subtree, the partial sums are folded back in tree order through shared memory.
+__global__ void __launch_bounds__(1024, 1)
+k_row_variance(int64_t K, int64_t F, const double *__restrict__ cm, double *__restrict__ variance)
 {
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ double red[1024];
+    const int64_t row = blockIdx.x;
     if (row >= K) return;
     const double *__restrict__ a = cm + row * F;
     auto at = [a](int64_t i) { return a[i]; };
-    const double mean = __ddiv_rn(pairwise_sum_warp(at, 0, F), (double)F);
+    const double mean = __ddiv_rn(pairwise_sum_block1024(at, 0, F, red), (double)F);
     auto at_sq = [a, mean](int64_t i) {
         const double x = __dadd_rn(a[i], -mean);
         return __dmul_rn(x, x);
     };
-    const double var = __ddiv_rn(pairwise_sum_warp(at_sq, 0, F), (double)F);
-    if (lane_id() == 0) variance[row] = var;
+    const double var = __ddiv_rn(pairwise_sum_block1024(at_sq, 0, F, red), (double)F);
+    if (threadIdx.x == 0) variance[row] = var;
 }
 
 // community_weighting.py:55-67: noise = sqrt(mean(variance)); per column the spread of its
@@ -302,7 +306,7 @@ static int peak_snr_device(arcte_cuda_ctx *c, int64_t K, int64_t F, double *cm, 
     const unsigned cap = (unsigned)c->sm_count * 16;
     if (g > cap) g = cap;
     k_nan_to_zero<<<g, 256, 0, st>>>(K * F, cm);
-    k_row_variance<<<wgrid(K * 32, 128), 128, 0, st>>>(K, F, cm, c->scratch[10].as<double>());
+    k_row_variance<<<(unsigned)K, 1024, 0, st>>>(K, F, cm, c->scratch[10].as<double>());
     k_psnr_weights<<<wgrid(F, 256), 256, 0, st>>>(K, F, cm, c->scratch[10].as<double>(), weights);
     c->stats.launches += 3;
     ARCTE_CUDA_TRY(cudaGetLastError());
