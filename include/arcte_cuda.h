@@ -51,6 +51,17 @@ enum {
                                  pagerank_lazy_push, push.py:20     (arcte_with_lazy_pagerank, arcte.py:391) */
 };
 
+/* Walk schedules of the push engine (arcte_cuda_set_schedule). */
+enum {
+    ARCTE_SCHEDULE_FIFO = 0,     /* exact replay of the reference's FIFO (similarity.py:199-216): s, r, push
+                                    counts and the thresholded support are bit-identical to the reference.  Default. */
+    ARCTE_SCHEDULE_FRONTIER = 1  /* synchronous frontier rounds on 64-bit fixed-point state, one CTA per seed:
+                                    every node over the threshold is pushed per round.  Same error bound
+                                    0 <= (G - s)/d < eps (1-rho)/rho; support identical to the reference up to
+                                    documented in-band ties; deterministic (independent of timing, sharding and
+                                    launch geometry).  Absorbing rule (arcte) only. */
+};
+
 /* Counters and device timings of the last arcte_cuda_extract/assemble on this context. */
 typedef struct arcte_cuda_stats {
     int64_t n_seeds_total;   /* seeds selected on the graph (arcte.py:614-617)              */
@@ -67,6 +78,7 @@ typedef struct arcte_cuda_stats {
     int64_t retries;         /* seeds re-run with a larger FIFO                               */
     int64_t n_slots;         /* concurrent per-warp walk states used                          */
     int64_t launches;        /* kernels launched by the last build/extract/assemble calls     */
+    int64_t rounds;          /* frontier schedule: synchronous rounds, summed over seeds      */
     double ms_transition;    /* K1: degrees + row normalisation                               */
     double ms_seeds;         /* K2: seed selection/ordering + epsilon-effective               */
     double ms_push;          /* K3+K4: fused push / threshold / compaction kernel             */
@@ -86,6 +98,14 @@ const char *arcte_cuda_last_error(void);
    demand (affected seeds are re-run), so small values are safe, only slower. */
 int arcte_cuda_configure(arcte_cuda_ctx *ctx, int warps_per_sm, int64_t queue_capacity,
                          int mem_percent, int64_t member_capacity);
+
+/* Selects the walk schedule of arcte_cuda_extract / arcte_cuda_push on this context.  The
+   remaining arguments tune the frontier schedule's launch geometry (0 or negative = default):
+   the first heavy_permille/1000 of the count-descending seed list is walked by
+   heavy_ctas_per_sm CTAs of heavy_threads threads per SM, the rest by light_ctas_per_sm CTAs of
+   light_threads threads (threads: 128, 256, 512 or 1024). */
+int arcte_cuda_set_schedule(arcte_cuda_ctx *ctx, int schedule, int heavy_permille, int heavy_threads,
+                            int heavy_ctas_per_sm, int light_threads, int light_ctas_per_sm);
 
 /* -- a11 + a1: graph upload and transition build --------------------------- */
 /* Replaces the pickled (indices, indptr, data) hand-off of arcte.py:657-665 and

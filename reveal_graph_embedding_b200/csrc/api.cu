@@ -118,7 +118,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->seeds,
                       &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
-                      &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->counters, &c->out_indptr,
+                      &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->slots.frontier, &c->slots.fval, &c->counters, &c->out_indptr,
                       &c->out_indices, &c->out_data};
     for (DevBuf *b : bufs) dev_free(*b);
     for (DevBuf &b : c->scratch) dev_free(b);
@@ -150,6 +150,25 @@ int arcte_cuda_configure(arcte_cuda_ctx *c, int warps_per_sm, int64_t queue_capa
     return ARCTE_OK;
 }
 
+int arcte_cuda_set_schedule(arcte_cuda_ctx *c, int schedule, int heavy_permille, int heavy_threads,
+                            int heavy_ctas_per_sm, int light_threads, int light_ctas_per_sm)
+{
+    CHECK_CTX(c);
+    auto threads_ok = [](int t) { return t <= 0 || t == 128 || t == 256 || t == 512 || t == 1024; };
+    if ((schedule != ARCTE_SCHEDULE_FIFO && schedule != ARCTE_SCHEDULE_FRONTIER) || heavy_permille > 1000 ||
+        !threads_ok(heavy_threads) || !threads_ok(light_threads) || heavy_ctas_per_sm > 32 || light_ctas_per_sm > 32) {
+        set_error("set_schedule: argument out of range");
+        return ARCTE_E_ARG;
+    }
+    c->schedule = schedule;
+    c->fr_heavy_permille = heavy_permille >= 0 ? heavy_permille : -1;
+    c->fr_heavy_threads = heavy_threads > 0 ? heavy_threads : 0;
+    c->fr_heavy_ctas = heavy_ctas_per_sm > 0 ? heavy_ctas_per_sm : 0;
+    c->fr_light_threads = light_threads > 0 ? light_threads : 0;
+    c->fr_light_ctas = light_ctas_per_sm > 0 ? light_ctas_per_sm : 0;
+    return ARCTE_OK;
+}
+
 int arcte_cuda_set_graph(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
                          const int32_t *host_indices, const double *host_data);
 
@@ -172,6 +191,8 @@ static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int
         dev_free(c->slots.sr);
         dev_free(c->slots.touched);
         dev_free(c->slots.queue);
+        dev_free(c->slots.frontier);
+        dev_free(c->slots.fval);
         c->slots = SlotPool();
     }
     c->n = n;

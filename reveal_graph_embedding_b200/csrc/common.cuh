@@ -56,6 +56,9 @@ struct SlotPool {
     DevBuf sr;       // double2 [n_slots][n]
     DevBuf touched;  // int32   [n_slots][n]
     DevBuf queue;    // int32   [n_slots][queue_cap]
+    DevBuf frontier; // int32   [frontier_slots][2][n]  (frontier schedule only)
+    DevBuf fval;     // double  [frontier_slots][n]     (frontier schedule only)
+    int64_t frontier_slots = 0;
     int64_t n_slots = 0;      // state/touched rows allocated
     int64_t queue_slots = 0;  // FIFO rings allocated (== n_slots except after a retry grew the rings)
     int64_t queue_cap = 0;
@@ -66,7 +69,7 @@ struct SlotPool {
 enum PushCounter {
     PC_PUSHES = 0, PC_EDGES, PC_ENQUEUES, PC_MAXQ, PC_SUPPORT, PC_TOUCHED, PC_SEEDDEG, PC_MEMBERS,
     PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR,
-    PC_T_START, PC_T_END, PC_T_BUSY, PC_COUNT
+    PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS, PC_COUNT
 };
 
 }  // namespace arcte
@@ -84,6 +87,8 @@ struct arcte_cuda_ctx {
     int64_t queue_cap_cfg = 0; // 0 = default
     int mem_percent = 0;       // 0 = default
     int64_t member_cap_cfg = 0; // 0 = default
+    int schedule = 0;          // ARCTE_SCHEDULE_FIFO (exact) or ARCTE_SCHEDULE_FRONTIER
+    int fr_heavy_permille = -1, fr_heavy_threads = 0, fr_heavy_ctas = 0, fr_light_threads = 0, fr_light_ctas = 0;
 
     // graph (adjacency + transition), all resident
     int64_t n = 0, nnz = 0;

@@ -21,40 +21,10 @@
 // within the push error bound.  Thousands of slots are in flight per GPU; seeds are
 // pulled from a degree-descending work list through one atomic counter.
 #include "common.cuh"
+#include "push.cuh"
 
 namespace arcte {
 
-struct PushParams {
-    int64_t n;
-    const NodeInfo *info;      // {d_in, row begin, row length} per node
-    const int32_t *indices;
-    const double *w;
-    // work list
-    const int32_t *work_seed;  // [n_work_total] seed node per position
-    const double *work_eps;    // [n_work_total]
-    const int32_t *work_ids;   // positions to run (retry pass) or nullptr = 0..n_work-1
-    int64_t n_work;
-    int retry_pass;
-    // slots
-    double2 *sr;
-    int32_t *touched;
-    int32_t *queue;
-    int64_t queue_cap;  // power of two
-    int64_t n_slots;
-    // outputs
-    int32_t *seg_count;
-    int64_t *seg_offset;
-    int32_t *members;
-    int64_t member_cap;
-    int32_t *retry_list;
-    unsigned long long *counters;
-    // rule constants, computed on the host exactly as Python evaluates them
-    double rho;            // rho
-    double one_minus_rho;  // (1-rho)
-    double lazy_b;         // (1-rho)*(1-lazy)
-    double lazy_c;         // (1-rho)*lazy
-    int debug_keep;        // operator seam: stop after the walk, leave s/r in slot 0
-};
 
 __device__ __forceinline__ double warp_min(double v)
 {
@@ -534,14 +504,20 @@ __global__ void k_gather_eps(int64_t n_work, int shard_rank, int shard_count,
 
 __global__ void k_split_and_reset(int64_t n, int64_t n_touched, double2 *__restrict__ sr,
                                   const int32_t *__restrict__ touched, double *__restrict__ s_out,
-                                  double *__restrict__ r_out, int phase)
+                                  double *__restrict__ r_out, int phase, double inv_scale)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (phase == 0) {
         if (i < n) {
-            const double2 v = sr[i];
-            s_out[i] = v.x;
-            r_out[i] = v.y;
+            if (inv_scale == 0.0) {
+                const double2 v = sr[i];
+                s_out[i] = v.x;
+                r_out[i] = v.y;
+            } else {  // frontier schedule: unsigned 64-bit fixed point
+                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(sr)[i];
+                s_out[i] = __dmul_rn(__ull2double_rn(v.x), inv_scale);
+                r_out[i] = __dmul_rn(__ull2double_rn(v.y), inv_scale);
+            }
         }
     } else if (i < n_touched) {
         sr[touched[i]] = make_double2(0.0, 0.0);
@@ -698,9 +674,19 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
 
     // ---- slot pool + member buffer ----
+    const bool frontier = c->schedule == ARCTE_SCHEDULE_FRONTIER;
+    if (frontier && rule != ARCTE_RULE_ABSORBING) {
+        set_error("extract: the frontier schedule implements the absorbing rule (arcte) only");
+        return ARCTE_E_ARG;
+    }
     int64_t n_slots = 0, qcap = 0;
-    ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap));
-    ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    if (frontier) {
+        ARCTE_TRY(frontier_plan_slots(c, S, &n_slots));
+        ARCTE_TRY(frontier_ensure_slots(c, n_slots));
+    } else {
+        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap));
+        ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    }
     if (c->member_cap == 0) {
         // default: a tenth of what is free now, never more than the n_seeds x n worst case
         size_t free_b = 0, total_b = 0;
@@ -740,6 +726,10 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     P.debug_keep = 0;
     // arcte.py:109: the lazy worker walks with lazy_rho = 0.5 rho / (1 - 0.5 rho)
     fill_rule_constants(P, rule == ARCTE_RULE_LAZY ? (rho * (0.5)) / (1.0 - (0.5 * rho)) : rho);
+    if (frontier) {
+        P.scale = frontier_scale(rho);
+        P.inv_scale = 1.0 / P.scale;
+    }
 
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.as<int64_t>() + PC_T_START, 0xff, sizeof(int64_t), st));
@@ -748,7 +738,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     ARCTE_CUDA_TRY(cudaEventCreate(&p0));
     ARCTE_CUDA_TRY(cudaEventCreate(&p1));
     ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
-    ARCTE_TRY(launch_push(c, rule, P));
+    if (frontier) ARCTE_TRY(frontier_launch(c, P, S, false));
+    else ARCTE_TRY(launch_push(c, rule, P));
     ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
 
     int64_t hc[PC_COUNT];
@@ -761,6 +752,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     stt.ms_push = ms;
     stt.n_slots = n_slots;
     // mean busy time of a walk state / span of the launch (1.0 = no idle tail)
+    stt.rounds = 0;
     stt.slot_utilisation = hc[PC_T_END] > hc[PC_T_START]
                                ? (double)hc[PC_T_BUSY] / ((double)n_slots * (double)(hc[PC_T_END] - hc[PC_T_START]))
                                : 0.0;
@@ -786,7 +778,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
             }
         }
         int64_t r_slots = ((n_retry + 7) / 8) * 8;
-        if (r_slots > c->slots.queue_slots) r_slots = c->slots.queue_slots;
+        if (frontier) r_slots = n_slots;
+        else if (r_slots > c->slots.queue_slots) r_slots = c->slots.queue_slots;
         int64_t r_qcap = c->slots.queue_cap;
         if (hc[PC_QOVERFLOW] > 0) {
             // a bigger ring for fewer walks: same bytes first, then grow
@@ -825,7 +818,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.members = c->members.as<int32_t>();
         P.member_cap = c->member_cap;
         ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
-        ARCTE_TRY(launch_push(c, rule, P));
+        if (frontier) ARCTE_TRY(frontier_launch(c, P, n_retry, true));
+        else ARCTE_TRY(launch_push(c, rule, P));
         ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
         ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
@@ -844,6 +838,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     stt.seed_degree = hc[PC_SEEDDEG];
     stt.members = hc[PC_MEMBERS];
     stt.emitted = hc[PC_EMITTED];
+    stt.rounds = hc[PC_ROUNDS];
     // sum_pushes(24 + 52 deg(u)) + sum_seeds(32 |supp| + 12 deg(seed) + 12 |comm|)
     stt.alg_bytes_push = 24.0 * stt.pushes + 52.0 * stt.edge_touches + 32.0 * stt.support +
                          12.0 * stt.seed_degree + 12.0 * stt.members;
@@ -859,9 +854,19 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
     if (!c->have_transition) { set_error("push: no transition matrix (call set_graph)"); return ARCTE_E_ARG; }
     if (seed < 0 || seed >= c->n) { set_error("push: seed out of range"); return ARCTE_E_ARG; }
     cudaStream_t st = c->stream;
+    const bool frontier = c->schedule == ARCTE_SCHEDULE_FRONTIER;
+    if (frontier && rule != ARCTE_RULE_ABSORBING) {
+        set_error("push: the frontier schedule implements the absorbing rule only");
+        return ARCTE_E_ARG;
+    }
     int64_t n_slots = 0, qcap = 0;
-    ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
-    ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    if (frontier) {
+        ARCTE_TRY(frontier_plan_slots(c, 1, &n_slots));
+        ARCTE_TRY(frontier_ensure_slots(c, n_slots));
+    } else {
+        ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
+        ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+    }
     ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * 4));
     ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * 4));
@@ -889,7 +894,15 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.counters = c->counters.as<unsigned long long>();
         P.debug_keep = 1;
         fill_rule_constants(P, rho);
-        ARCTE_TRY(launch_push(c, rule, P));
+        double inv_scale = 0.0;
+        if (frontier) {
+            P.scale = frontier_scale(rho);
+            P.inv_scale = inv_scale = 1.0 / P.scale;
+            P.cursor = PC_WORK_CURSOR;
+            ARCTE_TRY(frontier_launch(c, P, 1, false));
+        } else {
+            ARCTE_TRY(launch_push(c, rule, P));
+        }
         int64_t hc[PC_COUNT];
         ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
@@ -897,13 +910,13 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         double *s_dev = c->scratch[3].as<double>();
         double *r_dev = s_dev + c->n;
         if (hc[PC_OVERFLOW_SEEDS] == 0) {
-            k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0);
+            k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0, inv_scale);
             ++c->stats.launches;
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_s, s_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_r, r_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
         }
         if (nt > 0) {
-            k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1);
+            k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1, inv_scale);
             ++c->stats.launches;
         }
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));

@@ -1,0 +1,476 @@
+// push_frontier.cu -- the SECOND walk schedule of the push engine (opt-in): synchronous
+// frontier rounds on fixed-point state, one CTA per seed.
+//
+// Why it exists.  The exact FIFO replay of push.cu is bit-identical to the reference but its
+// pushes are sequential inside a seed, so thousands of walks must be in flight to hide memory
+// latency, their dense states (gigabytes) live in DRAM and the kernel runs at the random-access
+// rate of HBM.  The epsilon-push iteration does not depend on the push
+// order for its guarantees: any order keeps  s + sum_v r[v] (G_v - e_v) = G_seed  and ends with
+// r[v]/d_in[v] < eps everywhere, hence 0 <= (G_seed - s)[x]/d[x] < eps (1-rho)/rho  (SURVEY.md
+// section 8a, error-bound note) -- the tolerance BASELINE.json's north_star states.  This file
+// uses that freedom for parallelism INSIDE a seed: all nodes over the threshold are pushed
+// together, a whole CTA works on one seed, only a few hundred walks are in flight and the
+// sectors they touch stay in the 126 MB L2.
+//
+// Reference semantics kept (paths relative to /root/reference/reveal_graph_embedding/):
+//   initial state and the unconditional first push    eps_randomwalk/similarity.py:176-192
+//   push rule  c = (1-rho) r[u]; r[u] = 0; s[N] += c w; r[N] += c w   eps_randomwalk/push.py:56-64
+//   a node is pushed when r[v]/d_in[v] >= eps         eps_randomwalk/similarity.py:194-216
+//   threshold / membership / emission                 embedding/arcte/arcte.py:352-376
+// Deliberately different: the ORDER of pushes (rounds instead of a FIFO) and the number format
+// of s and r.
+//
+// Determinism.  Rounds are Jacobi steps: phase 1 takes the residual of every frontier node,
+// phase 2 distributes all of them; s and r are unsigned 64-bit fixed-point numbers (unit
+// 2^-F), so the atomic additions of a round commute exactly.  The state after every round,
+// the frontier SETS and therefore the communities do not depend on thread timing, CTA size,
+// walk-slot count or seed sharding; the test suite restates the schedule on the CPU and compares
+// bit for bit.  Against the reference the support
+// is identical up to documented in-band ties (tests/test_frontier_schedule.py).
+#include "common.cuh"
+#include "push.cuh"
+
+namespace arcte {
+
+namespace {
+
+constexpr int kSmallDeg = 64;    // rows up to this length: one 8-lane group per frontier node
+constexpr int kWarpDeg = 512;    // up to this length: one warp per node; longer rows: the whole CTA
+constexpr int kBigCap = 1024;    // frontier nodes deferred to the warp / CTA passes per round
+
+__device__ __forceinline__ unsigned long long ld_fixed(const unsigned long long *p) { return __ldcg(p); }
+__device__ __forceinline__ double fixed_to_double(unsigned long long x, double inv_scale)
+{
+    return __dmul_rn(__ull2double_rn(x), inv_scale);
+}
+// similarity.py:194 / :204 / :214: r[v] / in_degree[v] >= epsilon
+__device__ __forceinline__ bool over_threshold(unsigned long long r, double d_in, double eps, double inv_scale)
+{
+    return __ddiv_rn(fixed_to_double(r, inv_scale), d_in) >= eps;
+}
+
+struct WalkShared {
+    int cur_n, next_n, nt, big_n, m;
+    long long work;
+    long long off;
+    unsigned long long edges;
+    int big[kBigCap];
+    double red[32];
+    unsigned long long tot[10];  // pushes, edges, enqueues, max frontier, support, touched, seed degree, members, emitted, rounds
+};
+
+// One neighbour touch by every lane of the warp (inactive lanes pass pf = 0): push.py:63-64 with
+// atomics, first-touch bookkeeping and threshold-crossing detection.  Exactly one addition
+// moves r[v] across the threshold in a round (additions are positive and r[v] is not reset
+// during phase 2), so v enters the next frontier exactly once.
+__device__ __forceinline__ void touch(const PushParams &P, unsigned long long *__restrict__ sr,
+                                      int32_t *__restrict__ touched, int32_t *__restrict__ next, WalkShared &sh,
+                                      int v, unsigned long long pf, double eps, int lane, unsigned lt)
+{
+    bool is_new = false, cross = false;
+    if (pf) {
+        const unsigned long long old_s = atomicAdd(&sr[2 * (int64_t)v], pf);
+        const unsigned long long old_r = atomicAdd(&sr[2 * (int64_t)v + 1], pf);
+        const double d = P.info[v].d_in;
+        is_new = old_s == 0ull;
+        cross = !over_threshold(old_r, d, eps, P.inv_scale) && over_threshold(old_r + pf, d, eps, P.inv_scale);
+    }
+    const unsigned m_new = __ballot_sync(kFull, is_new);
+    if (m_new) {
+        int base = 0;
+        if (lane == __ffs(m_new) - 1) base = atomicAdd(&sh.nt, __popc(m_new));
+        base = __shfl_sync(kFull, base, __ffs(m_new) - 1);
+        if (is_new) touched[base + __popc(m_new & lt)] = v;
+    }
+    const unsigned m_x = __ballot_sync(kFull, cross);
+    if (m_x) {
+        int base = 0;
+        if (lane == __ffs(m_x) - 1) base = atomicAdd(&sh.next_n, __popc(m_x));
+        base = __shfl_sync(kFull, base, __ffs(m_x) - 1);
+        if (cross) next[base + __popc(m_x & lt)] = v;
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
+{
+    constexpr int NW = T / 32;
+    __shared__ WalkShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = lanemask_lt();
+    const int64_t slot = blockIdx.x;
+    if (slot >= P.n_slots) return;
+    unsigned long long *__restrict__ sr = reinterpret_cast<unsigned long long *>(P.sr + slot * P.n);
+    int32_t *__restrict__ touched = P.touched + slot * P.n;
+    int32_t *fa = P.frontier + slot * 2 * P.n;
+    int32_t *fb = fa + P.n;
+    double *__restrict__ fval = P.fval + slot * P.n;
+    if (tid < 10) sh.tot[tid] = 0ull;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) sh.work = (long long)atomicAdd(&P.counters[P.cursor], 1ull);
+        __syncthreads();
+        const long long k = sh.work;
+        if (k >= P.n_work) break;
+        const int pos = P.work_ids ? P.work_ids[k] : (int)(P.work_lo + k);
+        const int seed = P.work_seed[pos];
+        const double eps = P.work_eps[pos];
+        const unsigned long long one = (unsigned long long)__double2ll_rn(P.scale);
+
+        // similarity.py:176-177: s[seed] = r[seed] = 1; the seed is the first frontier
+        if (tid == 0) {
+            __stcg(&sr[2 * (int64_t)seed], one);
+            __stcg(&sr[2 * (int64_t)seed + 1], one);
+            touched[0] = seed;
+            fa[0] = seed;
+            sh.nt = 1;
+            sh.cur_n = 1;
+            sh.next_n = 0;
+            sh.big_n = 0;
+            sh.edges = 0ull;
+        }
+        __syncthreads();
+        int32_t *cur = fa, *next = fb;
+        unsigned long long pushes = 0, enq = 0, maxf = 0, rounds = 0;
+
+        for (;;) {
+            const int cur_n = sh.cur_n;
+            if (cur_n == 0) break;
+            // ---- phase 1: take the residual of every frontier node (push.py:57, :60) ----
+            unsigned long long my_edges = 0;
+            for (int i = tid; i < cur_n; i += T) {
+                const int u = cur[i];
+                const unsigned long long r = ld_fixed(&sr[2 * (int64_t)u + 1]);
+                __stcg(&sr[2 * (int64_t)u + 1], 0ull);
+                fval[i] = __dmul_rn(P.one_minus_rho, fixed_to_double(r, P.inv_scale));
+                my_edges += P.info[u].len;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_edges += __shfl_xor_sync(kFull, my_edges, o);
+            if (lane == 0 && my_edges) atomicAdd(&sh.edges, my_edges);
+            __syncthreads();
+
+            // ---- phase 2a: short rows, four frontier nodes per warp (8 lanes each) ----
+            for (int base_i = warp * 4; base_i < cur_n; base_i += NW * 4) {
+                const int i = base_i + (lane >> 3);
+                const bool valid = i < cur_n;
+                NodeInfo iu;
+                iu.d_in = 0.0; iu.begin = 0; iu.len = 0;
+                double c = 0.0;
+                if (valid) {
+                    iu = P.info[cur[i]];
+                    c = fval[i];
+                }
+                const bool big = valid && iu.len > (unsigned)kSmallDeg;
+                int got = 0;
+                if (big && (lane & 7) == 0) {
+                    const int b = atomicAdd(&sh.big_n, 1);
+                    got = b < kBigCap;
+                    if (got) sh.big[b] = i;
+                }
+                got = __shfl_sync(kFull, got, lane & ~7);
+                const unsigned mydeg = (valid && (!big || !got)) ? iu.len : 0u;  // a full deferral list falls back to this pass
+                unsigned maxdeg = mydeg;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, o));
+                for (unsigned j0 = 0; j0 < maxdeg; j0 += 8) {
+                    const unsigned j = j0 + (lane & 7);
+                    int v = 0;
+                    unsigned long long pf = 0ull;
+                    if (j < mydeg) {
+                        v = P.indices[iu.begin + j];
+                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
+                    }
+                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                }
+            }
+            __syncthreads();
+            // ---- phase 2b: medium rows, one warp per node; long rows, the whole CTA ----
+            const int big_n = min(sh.big_n, kBigCap);
+            for (int b = warp; b < big_n; b += NW) {
+                const int i = sh.big[b];
+                const NodeInfo iu = P.info[cur[i]];
+                if (iu.len > (unsigned)kWarpDeg) continue;
+                const double c = fval[i];
+                for (unsigned j0 = 0; j0 < iu.len; j0 += 32) {
+                    const unsigned j = j0 + lane;
+                    int v = 0;
+                    unsigned long long pf = 0ull;
+                    if (j < iu.len) {
+                        v = P.indices[iu.begin + j];
+                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
+                    }
+                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                }
+            }
+            for (int b = 0; b < big_n; ++b) {
+                const int i = sh.big[b];
+                const NodeInfo iu = P.info[cur[i]];
+                if (iu.len <= (unsigned)kWarpDeg) continue;
+                const double c = fval[i];
+                for (unsigned j0 = 0; j0 < iu.len; j0 += T) {
+                    const unsigned j = j0 + tid;
+                    int v = 0;
+                    unsigned long long pf = 0ull;
+                    if (j < iu.len) {
+                        v = P.indices[iu.begin + j];
+                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
+                    }
+                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                }
+            }
+            __syncthreads();
+            pushes += cur_n;
+            rounds += 1;
+            if ((unsigned long long)cur_n > maxf) maxf = cur_n;
+            enq += sh.next_n;
+            __syncthreads();
+            if (tid == 0) {
+                sh.cur_n = sh.next_n;
+                sh.next_n = 0;
+                sh.big_n = 0;
+            }
+            int32_t *t = cur; cur = next; next = t;
+            __syncthreads();
+        }
+
+        const int nt = sh.nt;
+        if (P.debug_keep) {
+            if (tid == 0) {
+                P.counters[PC_PUSHES] = pushes;
+                P.counters[PC_TOUCHED] = (unsigned long long)nt;
+                P.counters[PC_OVERFLOW_SEEDS] = 0ull;
+            }
+            return;
+        }
+
+        // ---------------- threshold + membership (arcte.py:352-376) ----------------
+        const NodeInfo si = P.info[seed];
+        const int base_size = (int)si.len + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
+        double q = __ddiv_rn(fixed_to_double(ld_fixed(&sr[2 * (int64_t)seed]), P.inv_scale), si.d_in);
+        for (unsigned j = tid; j < si.len; j += T) {
+            const int v = P.indices[si.begin + j];
+            q = fmin(q, __ddiv_rn(fixed_to_double(ld_fixed(&sr[2 * (int64_t)v]), P.inv_scale), P.info[v].d_in));  // arcte.py:355-356
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(kFull, q, o));
+        if (lane == 0) sh.red[warp] = q;
+        if (tid == 0) sh.m = 0;
+        __syncthreads();
+        double tau = sh.red[0];
+        for (int wv = 1; wv < NW; ++wv) tau = fmin(tau, sh.red[wv]);  // arcte.py:359-360
+        // one sweep over the touched list: members (s/d_in >= tau, ties included: arcte.py:363-367)
+        // are staged in the free frontier buffer, the state is zeroed (arcte.py:337-338)
+        int32_t *stage = cur;
+        for (int i0 = 0; i0 < nt; i0 += T) {
+            const int i = i0 + tid;
+            bool pass = false;
+            int x = 0;
+            if (i < nt) {
+                x = touched[i];
+                const unsigned long long sx = ld_fixed(&sr[2 * (int64_t)x]);
+                __stcg(reinterpret_cast<ulonglong2 *>(&sr[2 * (int64_t)x]), make_ulonglong2(0ull, 0ull));
+                pass = __ddiv_rn(fixed_to_double(sx, P.inv_scale), P.info[x].d_in) >= tau;
+            }
+            const unsigned mp = __ballot_sync(kFull, pass);
+            if (mp) {
+                int base = 0;
+                if (lane == __ffs(mp) - 1) base = atomicAdd(&sh.m, __popc(mp));
+                base = __shfl_sync(kFull, base, __ffs(mp) - 1);
+                if (pass) stage[base + __popc(mp & lt)] = x;
+            }
+        }
+        __syncthreads();
+        const int m = sh.m;
+        const bool emit = m > base_size;  // arcte.py:370
+        if (tid == 0) {
+            long long off = 0;
+            if (emit) {
+                if (P.retry_pass && P.seg_count[pos] > 0) off = P.seg_offset[pos];  // claimed by the pass that overflowed
+                else off = (long long)atomicAdd(&P.counters[PC_MEMBER_CURSOR], (unsigned long long)m);
+            }
+            sh.off = off;
+        }
+        __syncthreads();
+        const long long off = sh.off;
+        const bool write = emit && off + m <= P.member_cap;
+        if (write)
+            for (int i = tid; i < m; i += T) P.members[off + i] = stage[i];  // arcte.py:372-376
+        if (tid == 0) {
+            if (emit) {
+                P.seg_count[pos] = m;
+                P.seg_offset[pos] = off;
+                if (!write) {
+                    const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
+                    P.retry_list[r] = pos;
+                }
+            } else {
+                P.seg_count[pos] = 0;
+                P.seg_offset[pos] = 0;
+            }
+            if (!emit || write) {  // a seed whose members did not fit is re-run and counted then
+                sh.tot[0] += pushes;
+                sh.tot[1] += sh.edges;
+                sh.tot[2] += enq;
+                if (maxf > sh.tot[3]) sh.tot[3] = maxf;
+                sh.tot[4] += (unsigned long long)nt;
+                sh.tot[5] += (unsigned long long)nt;
+                sh.tot[6] += si.len;
+                if (emit) {
+                    sh.tot[7] += (unsigned long long)m;
+                    sh.tot[8] += 1;
+                }
+                sh.tot[9] += rounds;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (tid == 0 && !P.debug_keep) {
+        atomicAdd(&P.counters[PC_PUSHES], sh.tot[0]);
+        atomicAdd(&P.counters[PC_EDGES], sh.tot[1]);
+        atomicAdd(&P.counters[PC_ENQUEUES], sh.tot[2]);
+        atomicMax(&P.counters[PC_MAXQ], sh.tot[3]);
+        atomicAdd(&P.counters[PC_SUPPORT], sh.tot[4]);
+        atomicAdd(&P.counters[PC_TOUCHED], sh.tot[5]);
+        atomicAdd(&P.counters[PC_SEEDDEG], sh.tot[6]);
+        atomicAdd(&P.counters[PC_MEMBERS], sh.tot[7]);
+        atomicAdd(&P.counters[PC_EMITTED], sh.tot[8]);
+        atomicAdd(&P.counters[PC_ROUNDS], sh.tot[9]);
+    }
+}
+
+int launch_frontier_kernel(arcte_cuda_ctx *c, const PushParams &P, int threads, int64_t grid)
+{
+    if (grid < 1) return ARCTE_OK;
+    switch (threads) {
+    case 128: k_push_frontier<128><<<(unsigned)grid, 128, 0, c->stream>>>(P); break;
+    case 256: k_push_frontier<256><<<(unsigned)grid, 256, 0, c->stream>>>(P); break;
+    case 512: k_push_frontier<512><<<(unsigned)grid, 512, 0, c->stream>>>(P); break;
+    case 1024: k_push_frontier<1024><<<(unsigned)grid, 1024, 0, c->stream>>>(P); break;
+    default: set_error("frontier schedule: threads per walk must be 128, 256, 512 or 1024"); return ARCTE_E_ARG;
+    }
+    ++c->stats.launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    return ARCTE_OK;
+}
+
+// Launch geometry: the count-descending seed list starts with the long walks (tens of thousands
+// of touched nodes each), so its head is walked by few large CTAs and the rest by many small
+// ones; both keep the sectors in flight within L2.
+struct Geometry {
+    int heavy_threads, heavy_ctas, light_threads, light_ctas, heavy_permille;
+};
+Geometry geometry(const arcte_cuda_ctx *c)
+{
+    Geometry g;
+    g.heavy_permille = c->fr_heavy_permille >= 0 ? c->fr_heavy_permille : 120;
+    g.heavy_threads = c->fr_heavy_threads > 0 ? c->fr_heavy_threads : 512;
+    g.heavy_ctas = c->fr_heavy_ctas > 0 ? c->fr_heavy_ctas : 2;
+    g.light_threads = c->fr_light_threads > 0 ? c->fr_light_threads : 256;
+    g.light_ctas = c->fr_light_ctas > 0 ? c->fr_light_ctas : 4;
+    return g;
+}
+
+}  // namespace
+
+// F fractional bits such that s <= 1/rho (the geometric series of similarity.py:176-216) fits
+// 63 bits with one bit to spare.
+double frontier_scale(double rho)
+{
+    int f = 62;
+    double top = 1.0 / rho + 1.0;
+    while (top > 1.0 && f > 20) { top *= 0.5; --f; }
+    return ldexp(1.0, f);
+}
+
+int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots)
+{
+    const Geometry g = geometry(c);
+    int64_t want = (int64_t)c->sm_count * (g.heavy_ctas > g.light_ctas ? g.heavy_ctas : g.light_ctas);
+    if (want > n_work) want = n_work;
+    if (want < 1) want = 1;
+    if (c->slots.n == c->n && c->slots.n_slots >= want && c->slots.frontier_slots >= want) {
+        *n_slots = want;
+        return ARCTE_OK;
+    }
+    size_t free_b = 0, total_b = 0;
+    ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes + c->slots.frontier.bytes +
+              c->slots.fval.bytes;
+    const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
+    const double per_slot = 36.0 * (double)c->n;  // state 16 + touched 4 + two frontiers 8 + taken mass 8
+    const int64_t fit = (int64_t)((double)free_b * pct / 100.0 / per_slot);
+    if (fit < 1) {
+        set_error("not enough device memory for one frontier walk state of this graph");
+        return ARCTE_E_NOMEM;
+    }
+    if (want > fit) want = fit;
+    *n_slots = want;
+    return ARCTE_OK;
+}
+
+int frontier_ensure_slots(arcte_cuda_ctx *c, int64_t want)
+{
+    SlotPool &sp = c->slots;
+    if (!(sp.n == c->n && sp.n_slots >= want)) {
+        dev_free(sp.sr);
+        dev_free(sp.touched);
+        dev_free(sp.queue);
+        dev_free(sp.frontier);
+        dev_free(sp.fval);
+        sp.n_slots = sp.queue_slots = sp.frontier_slots = 0;
+        sp.queue_cap = 0;
+        ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)want * (size_t)c->n));
+        ARCTE_TRY(dev_reserve(sp.touched, sizeof(int32_t) * (size_t)want * (size_t)c->n));
+        ARCTE_CUDA_TRY(cudaMemsetAsync(sp.sr.p, 0, sizeof(double2) * (size_t)want * (size_t)c->n, c->stream));
+        sp.n = c->n;
+        sp.n_slots = want;
+    }
+    if (sp.frontier_slots < want) {
+        dev_free(sp.frontier);
+        dev_free(sp.fval);
+        ARCTE_TRY(dev_reserve(sp.frontier, sizeof(int32_t) * 2 * (size_t)want * (size_t)c->n));
+        ARCTE_TRY(dev_reserve(sp.fval, sizeof(double) * (size_t)want * (size_t)c->n));
+        sp.frontier_slots = want;
+    }
+    return ARCTE_OK;
+}
+
+// One pass over P.n_work positions: the head of the list with the heavy geometry, the rest with
+// the light one (a retry pass or a single seed: one launch).
+int frontier_launch(arcte_cuda_ctx *c, PushParams P, int64_t n_work, bool retry_pass)
+{
+    const Geometry g = geometry(c);
+    P.frontier = c->slots.frontier.as<int32_t>();
+    P.fval = c->slots.fval.as<double>();
+    const int64_t max_slots = P.n_slots;
+    int64_t n_heavy = retry_pass || P.debug_keep ? 0 : (n_work * g.heavy_permille) / 1000;
+    if (n_heavy > 0) {
+        PushParams H = P;
+        H.n_work = n_heavy;
+        H.work_lo = 0;
+        H.cursor = PC_WORK_CURSOR;
+        int64_t grid = (int64_t)c->sm_count * g.heavy_ctas;
+        if (grid > max_slots) grid = max_slots;
+        if (grid > n_heavy) grid = n_heavy;
+        H.n_slots = grid;
+        ARCTE_TRY(launch_frontier_kernel(c, H, g.heavy_threads, grid));
+    }
+    if (n_work - n_heavy > 0) {
+        PushParams L = P;
+        L.n_work = n_work - n_heavy;
+        L.work_lo = n_heavy;
+        L.cursor = n_heavy > 0 ? PC_WORK_CURSOR2 : PC_WORK_CURSOR;
+        if (P.work_ids) L.work_lo = 0;
+        int64_t grid = (int64_t)c->sm_count * g.light_ctas;
+        if (grid > max_slots) grid = max_slots;
+        if (grid > L.n_work) grid = L.n_work;
+        L.n_slots = grid;
+        ARCTE_TRY(launch_frontier_kernel(c, L, P.debug_keep ? g.heavy_threads : g.light_threads, grid));
+    }
+    return ARCTE_OK;
+}
+
+}  // namespace arcte

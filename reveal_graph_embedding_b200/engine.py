@@ -10,7 +10,35 @@ import numpy as np
 import scipy.sparse as sparse
 
 from . import _lib, hostmem
-from ._lib import RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, ArcteCudaError, check, ptr  # noqa: F401
+from ._lib import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, SCHEDULE_FIFO, SCHEDULE_FRONTIER,  # noqa: F401
+                   ArcteCudaError, check, ptr)
+
+_SCHEDULES = {"fifo": SCHEDULE_FIFO, "exact": SCHEDULE_FIFO, "frontier": SCHEDULE_FRONTIER,
+              SCHEDULE_FIFO: SCHEDULE_FIFO, SCHEDULE_FRONTIER: SCHEDULE_FRONTIER}
+_default_schedule = [None]  # set_default_schedule(); None = ARCTE_CUDA_SCHEDULE or "fifo"
+
+
+def set_default_schedule(schedule):
+    """Walk schedule of every engine created or fetched from now on: "fifo" (exact replay of
+    the reference's queue, the default) or "frontier" (synchronous fixed-point rounds:
+    deterministic, same error bound, support equal up to in-band ties; several times faster).
+    The environment variable ARCTE_CUDA_SCHEDULE sets the same default."""
+    if schedule is not None and schedule not in _SCHEDULES:
+        raise ValueError("unknown schedule %r" % (schedule,))
+    _default_schedule[0] = schedule
+    for e in _ENGINES.values():
+        if e._h is not None:
+            e.set_schedule(_resolve_schedule())
+
+
+def _resolve_schedule():
+    import os
+    name = _default_schedule[0]
+    if name is None:
+        name = os.environ.get("ARCTE_CUDA_SCHEDULE", "fifo").strip().lower() or "fifo"
+    if name not in _SCHEDULES:
+        raise ValueError("ARCTE_CUDA_SCHEDULE must be 'fifo' or 'frontier', got %r" % (name,))
+    return name
 
 
 def canonical_csr(adjacency_matrix):
@@ -36,6 +64,7 @@ class Engine:
         self.device = int(device)
         self.n = 0
         self.nnz = 0
+        self.schedule = SCHEDULE_FIFO
 
     def close(self):
         if getattr(self, "_h", None):
@@ -52,6 +81,16 @@ class Engine:
     def configure(self, warps_per_sm=0, queue_capacity=0, mem_percent=0, member_capacity=0):
         check(self._L.arcte_cuda_configure(self._h, int(warps_per_sm), int(queue_capacity), int(mem_percent),
                                            int(member_capacity)))
+
+    def set_schedule(self, schedule, heavy_permille=-1, heavy_threads=0, heavy_ctas_per_sm=0, light_threads=0,
+                     light_ctas_per_sm=0):
+        """"fifo" / "frontier" (include/arcte_cuda.h: ARCTE_SCHEDULE_*); the other arguments tune the
+        frontier schedule's launch geometry (defaults when 0 / negative)."""
+        if schedule not in _SCHEDULES:
+            raise ValueError("unknown schedule %r" % (schedule,))
+        check(self._L.arcte_cuda_set_schedule(self._h, _SCHEDULES[schedule], int(heavy_permille), int(heavy_threads),
+                                              int(heavy_ctas_per_sm), int(light_threads), int(light_ctas_per_sm)))
+        self.schedule = _SCHEDULES[schedule]
 
     # -- a11 + a1 -------------------------------------------------------------------------
     def set_graph(self, adjacency_matrix, canonical=False):
@@ -323,6 +362,9 @@ def get_engine(device=0):
     if e is None or e._h is None:
         e = Engine(device)
         _ENGINES[device] = e
+    want = _SCHEDULES[_resolve_schedule()]
+    if e.schedule != want:
+        e.set_schedule(want)
     return e
 
 
