@@ -34,10 +34,6 @@ namespace arcte {
 
 namespace {
 
-constexpr int kSmallDeg = 64;    // rows up to this length: one 8-lane group per frontier node
-constexpr int kWarpDeg = 512;    // up to this length: one warp per node; longer rows: the whole CTA
-constexpr int kBigCap = 1024;    // frontier nodes deferred to the warp / CTA passes per round
-
 __device__ __forceinline__ unsigned long long ld_fixed(const unsigned long long *p) { return __ldcg(p); }
 __device__ __forceinline__ double fixed_to_double(unsigned long long x, double inv_scale)
 {
@@ -49,45 +45,67 @@ __device__ __forceinline__ bool over_threshold(unsigned long long r, double d_in
     return __ddiv_rn(fixed_to_double(r, inv_scale), d_in) >= eps;
 }
 
-struct WalkShared {
-    int cur_n, next_n, nt, big_n, m;
+template <int T> struct WalkShared {
+    int cur_n, next_n, nt, m;
     long long work;
     long long off;
     unsigned long long edges;
-    int big[kBigCap];
+    unsigned wsum[32];
+    unsigned eoff[T];     // per frontier entry of the current chunk: first edge on the chunk's edge line
+    unsigned ebeg[T];     //   first CSR position of its row
+    double ec[T];          //   mass it distributes this round
     double red[32];
     unsigned long long tot[10];  // pushes, edges, enqueues, max frontier, support, touched, seed degree, members, emitted, rounds
 };
 
-// One neighbour touch by every lane of the warp (inactive lanes pass pf = 0): push.py:63-64 with
-// atomics, first-touch bookkeeping and threshold-crossing detection.  Exactly one addition
-// moves r[v] across the threshold in a round (additions are positive and r[v] is not reset
-// during phase 2), so v enters the next frontier exactly once.
-__device__ __forceinline__ void touch(const PushParams &P, unsigned long long *__restrict__ sr,
-                                      int32_t *__restrict__ touched, int32_t *__restrict__ next, WalkShared &sh,
-                                      int v, unsigned long long pf, double eps, int lane, unsigned lt)
+// Two neighbour touches per lane, all lanes of the warp together (inactive lanes pass pf = 0):
+// push.py:63-64 with atomics, first-touch bookkeeping and threshold-crossing detection.  Exactly
+// one addition moves r[v] across the threshold in a round (additions are positive and r[v] is
+// not reset during phase 2), so v enters the next frontier exactly once.  The exact threshold
+// test (two divisions) runs only when the new residual is within 1e-9 of the threshold or
+// above; below that the quotient cannot reach eps (the quotient is monotone and its rounding
+// error is 2^-53), so skipping the test cannot change the outcome.
+template <typename SH>
+__device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *__restrict__ sr,
+                                       int32_t *__restrict__ touched, int32_t *__restrict__ next, SH &sh,
+                                       const int (&v)[2], const unsigned long long (&pf)[2], double eps, int lane,
+                                       unsigned lt, bool second)
 {
-    bool is_new = false, cross = false;
-    if (pf) {
-        const unsigned long long old_s = atomicAdd(&sr[2 * (int64_t)v], pf);
-        const unsigned long long old_r = atomicAdd(&sr[2 * (int64_t)v + 1], pf);
-        const double d = P.info[v].d_in;
-        is_new = old_s == 0ull;
-        cross = !over_threshold(old_r, d, eps, P.inv_scale) && over_threshold(old_r + pf, d, eps, P.inv_scale);
+    unsigned long long old_s[2], old_r[2];
+    double d[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (pf[k]) {
+            old_s[k] = atomicAdd(&sr[2 * (int64_t)v[k]], pf[k]);
+            old_r[k] = atomicAdd(&sr[2 * (int64_t)v[k] + 1], pf[k]);
+            d[k] = P.info[v[k]].d_in;
+        }
     }
-    const unsigned m_new = __ballot_sync(kFull, is_new);
-    if (m_new) {
-        int base = 0;
-        if (lane == __ffs(m_new) - 1) base = atomicAdd(&sh.nt, __popc(m_new));
-        base = __shfl_sync(kFull, base, __ffs(m_new) - 1);
-        if (is_new) touched[base + __popc(m_new & lt)] = v;
-    }
-    const unsigned m_x = __ballot_sync(kFull, cross);
-    if (m_x) {
-        int base = 0;
-        if (lane == __ffs(m_x) - 1) base = atomicAdd(&sh.next_n, __popc(m_x));
-        base = __shfl_sync(kFull, base, __ffs(m_x) - 1);
-        if (cross) next[base + __popc(m_x & lt)] = v;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !second) break;  // warp-uniform
+        bool is_new = false, cross = false;
+        if (pf[k]) {
+            is_new = old_s[k] == 0ull;
+            const double rn = fixed_to_double(old_r[k] + pf[k], P.inv_scale);
+            if (rn >= __dmul_rn(__dmul_rn(eps, d[k]), 0.999999999))
+                cross = over_threshold(old_r[k] + pf[k], d[k], eps, P.inv_scale) &&
+                        !over_threshold(old_r[k], d[k], eps, P.inv_scale);
+        }
+        const unsigned m_new = __ballot_sync(kFull, is_new);
+        if (m_new) {
+            int base = 0;
+            if (lane == __ffs(m_new) - 1) base = atomicAdd(&sh.nt, __popc(m_new));
+            base = __shfl_sync(kFull, base, __ffs(m_new) - 1);
+            if (is_new) touched[base + __popc(m_new & lt)] = v[k];
+        }
+        const unsigned m_x = __ballot_sync(kFull, cross);
+        if (m_x) {
+            int base = 0;
+            if (lane == __ffs(m_x) - 1) base = atomicAdd(&sh.next_n, __popc(m_x));
+            base = __shfl_sync(kFull, base, __ffs(m_x) - 1);
+            if (cross) next[base + __popc(m_x & lt)] = v[k];
+        }
     }
 }
 
@@ -95,7 +113,7 @@ template <int T>
 __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
 {
     constexpr int NW = T / 32;
-    __shared__ WalkShared sh;
+    __shared__ WalkShared<T> sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
     const int64_t slot = blockIdx.x;
@@ -127,7 +145,6 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             sh.nt = 1;
             sh.cur_n = 1;
             sh.next_n = 0;
-            sh.big_n = 0;
             sh.edges = 0ull;
         }
         __syncthreads();
@@ -151,76 +168,63 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             if (lane == 0 && my_edges) atomicAdd(&sh.edges, my_edges);
             __syncthreads();
 
-            // ---- phase 2a: short rows, four frontier nodes per warp (8 lanes each) ----
-            for (int base_i = warp * 4; base_i < cur_n; base_i += NW * 4) {
-                const int i = base_i + (lane >> 3);
-                const bool valid = i < cur_n;
-                NodeInfo iu;
-                iu.d_in = 0.0; iu.begin = 0; iu.len = 0;
+            // ---- phase 2: distribute (push.py:63-64), edge-balanced.  The frontier is taken T entries
+            // at a time: each thread loads one entry's row and mass, a CTA-wide exclusive scan of the
+            // row lengths lays the chunk's edges out on a line, and the threads walk that line T (x2)
+            // edges at a time, finding the owning entry by binary search in shared memory.  Every lane
+            // has an edge whatever the degree mix of the frontier. ----
+            for (int c0 = 0; c0 < cur_n; c0 += T) {
+                const int i = c0 + tid;
+                unsigned len = 0, beg = 0;
                 double c = 0.0;
-                if (valid) {
-                    iu = P.info[cur[i]];
+                if (i < cur_n) {
+                    const NodeInfo iu = P.info[cur[i]];
+                    len = iu.len;
+                    beg = iu.begin;
                     c = fval[i];
                 }
-                const bool big = valid && iu.len > (unsigned)kSmallDeg;
-                int got = 0;
-                if (big && (lane & 7) == 0) {
-                    const int b = atomicAdd(&sh.big_n, 1);
-                    got = b < kBigCap;
-                    if (got) sh.big[b] = i;
-                }
-                got = __shfl_sync(kFull, got, lane & ~7);
-                const unsigned mydeg = (valid && (!big || !got)) ? iu.len : 0u;  // a full deferral list falls back to this pass
-                unsigned maxdeg = mydeg;
+                // exclusive scan of len over the CTA
+                unsigned incl = len;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, o));
-                for (unsigned j0 = 0; j0 < maxdeg; j0 += 8) {
-                    const unsigned j = j0 + (lane & 7);
-                    int v = 0;
-                    unsigned long long pf = 0ull;
-                    if (j < mydeg) {
-                        v = P.indices[iu.begin + j];
-                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
-                    }
-                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += t;
                 }
-            }
-            __syncthreads();
-            // ---- phase 2b: medium rows, one warp per node; long rows, the whole CTA ----
-            const int big_n = min(sh.big_n, kBigCap);
-            for (int b = warp; b < big_n; b += NW) {
-                const int i = sh.big[b];
-                const NodeInfo iu = P.info[cur[i]];
-                if (iu.len > (unsigned)kWarpDeg) continue;
-                const double c = fval[i];
-                for (unsigned j0 = 0; j0 < iu.len; j0 += 32) {
-                    const unsigned j = j0 + lane;
-                    int v = 0;
-                    unsigned long long pf = 0ull;
-                    if (j < iu.len) {
-                        v = P.indices[iu.begin + j];
-                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
-                    }
-                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                if (lane == 31) sh.wsum[warp] = incl;
+                __syncthreads();
+                unsigned wbase = 0, total = 0;
+                for (int wv = 0; wv < NW; ++wv) {
+                    const unsigned t = sh.wsum[wv];
+                    if (wv < warp) wbase += t;
+                    total += t;
                 }
-            }
-            for (int b = 0; b < big_n; ++b) {
-                const int i = sh.big[b];
-                const NodeInfo iu = P.info[cur[i]];
-                if (iu.len <= (unsigned)kWarpDeg) continue;
-                const double c = fval[i];
-                for (unsigned j0 = 0; j0 < iu.len; j0 += T) {
-                    const unsigned j = j0 + tid;
-                    int v = 0;
-                    unsigned long long pf = 0ull;
-                    if (j < iu.len) {
-                        v = P.indices[iu.begin + j];
-                        pf = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(c, P.w[iu.begin + j]), P.scale));
+                sh.eoff[tid] = wbase + incl - len;
+                sh.ebeg[tid] = beg;
+                sh.ec[tid] = c;
+                __syncthreads();
+                for (unsigned e0 = 0; e0 < total; e0 += 2 * T) {
+                    int v[2];
+                    unsigned long long pf[2];
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const unsigned e = e0 + k2 * T + tid;
+                        v[k2] = 0;
+                        pf[k2] = 0ull;
+                        if (e < total) {
+                            int lo = 0, hi = T - 1;  // largest entry with eoff <= e
+                            while (lo < hi) {
+                                const int mid = (lo + hi + 1) >> 1;
+                                if (sh.eoff[mid] <= e) lo = mid; else hi = mid - 1;
+                            }
+                            const unsigned j = sh.ebeg[lo] + (e - sh.eoff[lo]);
+                            v[k2] = P.indices[j];
+                            pf[k2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(sh.ec[lo], P.w[j]), P.scale));
+                        }
                     }
-                    touch(P, sr, touched, next, sh, v, pf, eps, lane, lt);
+                    touch2(P, sr, touched, next, sh, v, pf, eps, lane, lt, e0 + T < total);
                 }
+                __syncthreads();
             }
-            __syncthreads();
             pushes += cur_n;
             rounds += 1;
             if ((unsigned long long)cur_n > maxf) maxf = cur_n;
@@ -229,8 +233,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             if (tid == 0) {
                 sh.cur_n = sh.next_n;
                 sh.next_n = 0;
-                sh.big_n = 0;
-            }
+                }
             int32_t *t = cur; cur = next; next = t;
             __syncthreads();
         }
