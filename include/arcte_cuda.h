@@ -103,7 +103,7 @@ int arcte_cuda_configure(arcte_cuda_ctx *ctx, int warps_per_sm, int64_t queue_ca
    remaining arguments tune the frontier schedule's launch geometry (0 or negative = default):
    the first heavy_permille/1000 of the count-descending seed list is walked by
    heavy_ctas_per_sm CTAs of heavy_threads threads per SM, the rest by light_ctas_per_sm CTAs of
-   light_threads threads (threads: 128, 256, 512 or 1024). */
+   light_threads threads (threads: 32, 64, 128, 256, 512 or 1024). */
 int arcte_cuda_set_schedule(arcte_cuda_ctx *ctx, int schedule, int heavy_permille, int heavy_threads,
                             int heavy_ctas_per_sm, int light_threads, int light_ctas_per_sm);
 

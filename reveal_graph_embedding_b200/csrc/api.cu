@@ -154,7 +154,7 @@ int arcte_cuda_set_schedule(arcte_cuda_ctx *c, int schedule, int heavy_permille,
                             int heavy_ctas_per_sm, int light_threads, int light_ctas_per_sm)
 {
     CHECK_CTX(c);
-    auto threads_ok = [](int t) { return t <= 0 || t == 128 || t == 256 || t == 512 || t == 1024; };
+    auto threads_ok = [](int t) { return t <= 0 || t == 32 || t == 64 || t == 128 || t == 256 || t == 512 || t == 1024; };
     if ((schedule != ARCTE_SCHEDULE_FIFO && schedule != ARCTE_SCHEDULE_FRONTIER) || heavy_permille > 1000 ||
         !threads_ok(heavy_threads) || !threads_ok(light_threads) || heavy_ctas_per_sm > 32 || light_ctas_per_sm > 32) {
         set_error("set_schedule: argument out of range");

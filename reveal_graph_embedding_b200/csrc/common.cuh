@@ -69,7 +69,9 @@ struct SlotPool {
 enum PushCounter {
     PC_PUSHES = 0, PC_EDGES, PC_ENQUEUES, PC_MAXQ, PC_SUPPORT, PC_TOUCHED, PC_SEEDDEG, PC_MEMBERS,
     PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR,
-    PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS, PC_COUNT
+    PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS,
+    PC_PROF0, PC_PROF1, PC_PROF2, PC_PROF3, PC_PROF4, PC_PROF5, PC_PROF6, PC_PROF7, PC_PROF8, PC_PROF9,  // kernel experiments
+    PC_COUNT
 };
 
 }  // namespace arcte

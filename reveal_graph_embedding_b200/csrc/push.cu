@@ -20,6 +20,8 @@
 // r are bit-identical to numpy's and the thresholded support is identical, not merely
 // within the push error bound.  Thousands of slots are in flight per GPU; seeds are
 // pulled from a degree-descending work list through one atomic counter.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "push.cuh"
 
@@ -829,6 +831,11 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     cudaEventDestroy(p0);
     cudaEventDestroy(p1);
 
+    if (getenv("ARCTE_CUDA_PROFILE")) {  // per-phase clock sums of instrumented kernel builds
+        fprintf(stderr, "[arcte] profile counters:");
+        for (int k = PC_PROF0; k <= PC_PROF9; ++k) fprintf(stderr, " %lld", (long long)hc[k]);
+        fprintf(stderr, "\n");
+    }
     stt.pushes = hc[PC_PUSHES];
     stt.edge_touches = hc[PC_EDGES];
     stt.enqueues = hc[PC_ENQUEUES];

@@ -30,6 +30,20 @@
 #include "common.cuh"
 #include "push.cuh"
 
+#ifndef ARCTE_FRONTIER_PRELOAD
+#define ARCTE_FRONTIER_PRELOAD 0
+#endif
+
+#ifdef ARCTE_FRONTIER_PROFILE
+#define PROF_DECL long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
+#define PROF(k) do { const long long _n = clock64(); prof[k] += _n - prof_t; prof_t = _n; } while (0)
+#define PROF_COUNT(k, x) prof[k] += (x)
+#else
+#define PROF_DECL
+#define PROF(k) do { } while (0)
+#define PROF_COUNT(k, x) do { } while (0)
+#endif
+
 namespace arcte {
 
 namespace {
@@ -71,13 +85,27 @@ __device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *
                                        const int (&v)[2], const unsigned long long (&pf)[2], double eps, int lane,
                                        unsigned lt, bool second)
 {
-    unsigned long long old_s[2], old_r[2];
+    unsigned long long old_s[2], old_r[2], add[2];
     double d[2];
+#if ARCTE_FRONTIER_PRELOAD
+    // Experiment switch (default off, measured neutral: profiles/r1_frontier_schedule.md): fetch
+    // the pair with an ordinary load first and make the atomics depend on it, so that they hit
+    // L2.  (s < 2^63 always: the shifted value is zero.)
+    ulonglong2 pre[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (pf[k]) pre[k] = __ldcg(reinterpret_cast<const ulonglong2 *>(&sr[2 * (int64_t)v[k]]));
+#pragma unroll
+    for (int k = 0; k < 2; ++k) add[k] = pf[k] ? pf[k] + (pre[k].x >> 63) : 0ull;
+#else
+#pragma unroll
+    for (int k = 0; k < 2; ++k) add[k] = pf[k];
+#endif
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (pf[k]) {
-            old_s[k] = atomicAdd(&sr[2 * (int64_t)v[k]], pf[k]);
-            old_r[k] = atomicAdd(&sr[2 * (int64_t)v[k] + 1], pf[k]);
+            old_s[k] = atomicAdd(&sr[2 * (int64_t)v[k]], add[k]);
+            old_r[k] = atomicAdd(&sr[2 * (int64_t)v[k] + 1], add[k]);
             d[k] = P.info[v[k]].d_in;
         }
     }
@@ -125,6 +153,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
     double *__restrict__ fval = P.fval + slot * P.n;
     if (tid < 10) sh.tot[tid] = 0ull;
     __syncthreads();
+    PROF_DECL
 
     for (;;) {
         if (tid == 0) sh.work = (long long)atomicAdd(&P.counters[P.cursor], 1ull);
@@ -150,6 +179,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
         __syncthreads();
         int32_t *cur = fa, *next = fb;
         unsigned long long pushes = 0, enq = 0, maxf = 0, rounds = 0;
+        PROF(0);  // fetch + init
 
         for (;;) {
             const int cur_n = sh.cur_n;
@@ -167,6 +197,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             for (int o = 16; o > 0; o >>= 1) my_edges += __shfl_xor_sync(kFull, my_edges, o);
             if (lane == 0 && my_edges) atomicAdd(&sh.edges, my_edges);
             __syncthreads();
+            PROF(1);  // phase 1
 
             // ---- phase 2: distribute (push.py:63-64), edge-balanced.  The frontier is taken T entries
             // at a time: each thread loads one entry's row and mass, a CTA-wide exclusive scan of the
@@ -202,6 +233,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
                 sh.ebeg[tid] = beg;
                 sh.ec[tid] = c;
                 __syncthreads();
+                PROF(2);  // chunk load + scan
                 for (unsigned e0 = 0; e0 < total; e0 += 2 * T) {
                     int v[2];
                     unsigned long long pf[2];
@@ -222,8 +254,11 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
                         }
                     }
                     touch2(P, sr, touched, next, sh, v, pf, eps, lane, lt, e0 + T < total);
+                    PROF_COUNT(8, 1);
                 }
+                PROF(3);  // edge loop (this thread)
                 __syncthreads();
+                PROF(4);  // waiting for the other warps
             }
             pushes += cur_n;
             rounds += 1;
@@ -236,6 +271,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
                 }
             int32_t *t = cur; cur = next; next = t;
             __syncthreads();
+            PROF(5);  // round bookkeeping
         }
 
         const int nt = sh.nt;
@@ -285,6 +321,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             }
         }
         __syncthreads();
+        PROF(6);  // tau + sweep
         const int m = sh.m;
         const bool emit = m > base_size;  // arcte.py:370
         if (tid == 0) {
@@ -328,7 +365,12 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             }
         }
         __syncthreads();
+        PROF(7);  // emit
     }
+#ifdef ARCTE_FRONTIER_PROFILE
+    if (tid == 0)
+        for (int k = 0; k < 10; ++k) atomicAdd(&P.counters[PC_PROF0 + k], (unsigned long long)prof[k]);
+#endif
 
     if (tid == 0 && !P.debug_keep) {
         atomicAdd(&P.counters[PC_PUSHES], sh.tot[0]);
@@ -348,31 +390,34 @@ int launch_frontier_kernel(arcte_cuda_ctx *c, const PushParams &P, int threads, 
 {
     if (grid < 1) return ARCTE_OK;
     switch (threads) {
+    case 32: k_push_frontier<32><<<(unsigned)grid, 32, 0, c->stream>>>(P); break;
+    case 64: k_push_frontier<64><<<(unsigned)grid, 64, 0, c->stream>>>(P); break;
     case 128: k_push_frontier<128><<<(unsigned)grid, 128, 0, c->stream>>>(P); break;
     case 256: k_push_frontier<256><<<(unsigned)grid, 256, 0, c->stream>>>(P); break;
     case 512: k_push_frontier<512><<<(unsigned)grid, 512, 0, c->stream>>>(P); break;
     case 1024: k_push_frontier<1024><<<(unsigned)grid, 1024, 0, c->stream>>>(P); break;
-    default: set_error("frontier schedule: threads per walk must be 128, 256, 512 or 1024"); return ARCTE_E_ARG;
+    default: set_error("frontier schedule: threads per walk must be 32, 64, 128, 256, 512 or 1024"); return ARCTE_E_ARG;
     }
     ++c->stats.launches;
     ARCTE_CUDA_TRY(cudaGetLastError());
     return ARCTE_OK;
 }
 
-// Launch geometry: the count-descending seed list starts with the long walks (tens of thousands
-// of touched nodes each), so its head is walked by few large CTAs and the rest by many small
-// ones; both keep the sectors in flight within L2.
+// Launch geometry: the head of the count-descending seed list (the long walks) can be given
+// fewer, larger CTAs than the rest.  Measured on the YouTube shape the geometry hardly matters
+// (3.9-4.9 s from 296 walks of 512 threads to 2580 walks of 32 threads), so by default every
+// seed is walked by 64 threads, 16 walks per SM (profiles/r1_frontier_schedule.md).
 struct Geometry {
     int heavy_threads, heavy_ctas, light_threads, light_ctas, heavy_permille;
 };
 Geometry geometry(const arcte_cuda_ctx *c)
 {
     Geometry g;
-    g.heavy_permille = c->fr_heavy_permille >= 0 ? c->fr_heavy_permille : 120;
+    g.heavy_permille = c->fr_heavy_permille >= 0 ? c->fr_heavy_permille : 0;
     g.heavy_threads = c->fr_heavy_threads > 0 ? c->fr_heavy_threads : 512;
     g.heavy_ctas = c->fr_heavy_ctas > 0 ? c->fr_heavy_ctas : 2;
-    g.light_threads = c->fr_light_threads > 0 ? c->fr_light_threads : 256;
-    g.light_ctas = c->fr_light_ctas > 0 ? c->fr_light_ctas : 4;
+    g.light_threads = c->fr_light_threads > 0 ? c->fr_light_threads : 64;
+    g.light_ctas = c->fr_light_ctas > 0 ? c->fr_light_ctas : 16;
     return g;
 }
 
