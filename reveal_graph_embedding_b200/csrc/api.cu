@@ -116,7 +116,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->seeds,
+    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->edge_wd, &c->seeds,
                       &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
                       &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->slots.frontier, &c->slots.fval, &c->counters, &c->out_indptr,
                       &c->out_indices, &c->out_data};

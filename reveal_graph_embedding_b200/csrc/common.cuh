@@ -10,6 +10,13 @@
 
 #include "../../include/arcte_cuda.h"
 
+// Experiment switch (default off, measured neutral on both bench shapes: profiles/README.md):
+// 1 = the push kernel reads {weight, in-degree of the target} as one coalesced 16-byte record per
+// stored entry instead of the weight array plus a random gather of the target's node record.
+#ifndef ARCTE_EDGE_RECORDS
+#define ARCTE_EDGE_RECORDS 0
+#endif
+
 namespace arcte {
 
 constexpr int kWarp = 32;
@@ -102,6 +109,7 @@ struct arcte_cuda_ctx {
     arcte::DevBuf d_in;     // double [n]
     arcte::DevBuf colcnt;   // int32 [n]  binarised column counts
     arcte::DevBuf node_info; // NodeInfo [n]
+    arcte::DevBuf edge_wd;   // double2 [nnz]  {transition weight, in-degree of the target} per stored entry
     bool have_graph = false, have_transition = false;
 
     // seeds

@@ -170,28 +170,40 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
     __syncwarp();
     const unsigned qmask = (unsigned)P.queue_cap - 1u;
     const int32_t *__restrict__ idx = P.indices + begin;
+#if ARCTE_EDGE_RECORDS
+    const double2 *__restrict__ wd = P.wd + begin;
+#else
     const double *__restrict__ wgt = P.w + begin;
+#endif
     for (unsigned base = 0; base < len; base += 32 * kPushUnroll) {
         // phase 1: neighbour ids and transition weights of up to kPushUnroll chunks
         int v[kPushUnroll];
         double p[kPushUnroll];
+        double dv[kPushUnroll];
 #pragma unroll
         for (int k = 0; k < kPushUnroll; ++k) {
             const unsigned j = base + k * 32 + lane;
             v[k] = -1;
             if (j < len) {
                 v[k] = ld_index(idx + j);
+#if ARCTE_EDGE_RECORDS
+                const double2 e = wd[j];  // one coalesced 16-byte read: weight and the target's in-degree
+                p[k] = __dmul_rn(c, e.x);
+                dv[k] = e.y;
+#else
                 p[k] = __dmul_rn(c, ld_weight(wgt + j));
+#endif
             }
         }
-        // phase 2: their state pairs and in-degrees (independent gathers, all in flight)
+        // phase 2: their state pairs (independent gathers, all in flight)
         double2 o[kPushUnroll];
-        double dv[kPushUnroll];
 #pragma unroll
         for (int k = 0; k < kPushUnroll; ++k) {
             if (v[k] >= 0) {
                 o[k] = ld_state(&sr[v[k]]);
+#if !ARCTE_EDGE_RECORDS
                 dv[k] = ld_info_din(&P.info[v[k]]);
+#endif
             }
         }
         // phase 3: update and store (neighbours of one node are distinct: no ordering needed)
@@ -709,6 +721,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     P.info = c->node_info.as<NodeInfo>();
     P.indices = c->indices.as<int32_t>();
     P.w = c->w.as<double>();
+    P.wd = c->edge_wd.as<double2>();
     P.work_seed = c->work_seed.as<int32_t>();
     P.work_eps = c->work_eps.as<double>();
     P.work_ids = nullptr;
@@ -890,6 +903,7 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.info = c->node_info.as<NodeInfo>();
         P.indices = c->indices.as<int32_t>();
         P.w = c->w.as<double>();
+        P.wd = c->edge_wd.as<double2>();
         P.work_seed = c->scratch[0].as<int32_t>();
         P.work_eps = c->scratch[2].as<double>();
         P.n_work = 1;

@@ -12,6 +12,7 @@ struct PushParams {
     const NodeInfo *info;      // {d_in, row begin, row length} per node
     const int32_t *indices;
     const double *w;
+    const double2 *wd;         // {w, d_in of the target} per stored entry (FIFO schedule)
     // work list
     const int32_t *work_seed;  // [n_work_total] seed node per position
     const double *work_eps;    // [n_work_total]

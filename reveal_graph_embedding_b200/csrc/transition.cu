@@ -107,6 +107,18 @@ k_node_info(int64_t n, const int64_t *__restrict__ indptr, const double *__restr
     info[i] = r;
 }
 
+// ---- K1f: per-edge record {w_uv, d_in[v]} for the push kernel: the in-degree the enqueue test
+// needs (similarity.py:194 / :214) arrives with the coalesced read of the row instead of through
+// a second random gather per neighbour ----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_edge_records(int64_t nnz, const int32_t *__restrict__ indices, const double *__restrict__ w,
+               const double *__restrict__ d_in, double2 *__restrict__ wd)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += stride)
+        wd[j] = make_double2(w[j], d_in[indices[j]]);
+}
+
 // ---- K2a: seed keys -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_count_stats(int64_t n, const int32_t *__restrict__ colcnt, int64_t *__restrict__ out /*[2]: max, n_seeds*/)
@@ -219,6 +231,16 @@ int select_seeds(arcte_cuda_ctx *c)
     k_node_info<<<grid_for(n, 256), 256, 0, st>>>(n, c->indptr.as<int64_t>(), c->d_in.as<double>(),
                                                   c->node_info.as<NodeInfo>());
     ++*launches;
+#if ARCTE_EDGE_RECORDS
+    ARCTE_TRY(dev_reserve(c->edge_wd, sizeof(double2) * (size_t)(c->nnz > 0 ? c->nnz : 1)));
+    if (c->nnz > 0) {
+        unsigned g = grid_for(c->nnz, 256);
+        if (g > (unsigned)c->sm_count * 16) g = (unsigned)c->sm_count * 16;
+        k_edge_records<<<g, 256, 0, st>>>(c->nnz, c->indices.as<int32_t>(), c->w.as<double>(), c->d_in.as<double>(),
+                                          c->edge_wd.as<double2>());
+        ++*launches;
+    }
+#endif
     const size_t m = (size_t)n + 1;
     ARCTE_TRY(dev_reserve(c->seeds, sizeof(int32_t) * (size_t)n));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * m));
