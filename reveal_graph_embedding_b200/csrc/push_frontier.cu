@@ -38,10 +38,14 @@
 #define PROF_DECL long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64();
 #define PROF(k) do { const long long _n = clock64(); prof[k] += _n - prof_t; prof_t = _n; } while (0)
 #define PROF_COUNT(k, x) prof[k] += (x)
+#define PROF_PARAMS , long long *prof, long long &prof_t
+#define PROF_ARGS , prof, prof_t
 #else
 #define PROF_DECL
 #define PROF(k) do { } while (0)
 #define PROF_COUNT(k, x) do { } while (0)
+#define PROF_PARAMS
+#define PROF_ARGS
 #endif
 
 namespace arcte {
@@ -83,7 +87,7 @@ template <typename SH>
 __device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *__restrict__ sr,
                                        int32_t *__restrict__ touched, int32_t *__restrict__ next, SH &sh,
                                        const int (&v)[2], const unsigned long long (&pf)[2], double eps, int lane,
-                                       unsigned lt, bool second)
+                                       unsigned lt, bool second PROF_PARAMS)
 {
     unsigned long long old_s[2], old_r[2], add[2];
     double d[2];
@@ -109,6 +113,10 @@ __device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *
             d[k] = P.info[v[k]].d_in;
         }
     }
+#ifdef ARCTE_FRONTIER_PROFILE
+    if (((old_s[0] ^ old_r[0] ^ old_s[1] ^ old_r[1]) == 0x123456789abcdefull) || d[0] + d[1] == -1.0) prof[9] += 1;  // consume
+    PROF(9);  // atomics + in-degree returned
+#endif
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (k == 1 && !second) break;  // warp-uniform
@@ -253,7 +261,11 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
                             pf[k2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(sh.ec[lo], P.w[j]), P.scale));
                         }
                     }
-                    touch2(P, sr, touched, next, sh, v, pf, eps, lane, lt, e0 + T < total);
+#ifdef ARCTE_FRONTIER_PROFILE
+                    if ((pf[0] ^ pf[1]) == 0x123456789abcdefull) prof[7] += 1;  // consume
+                    PROF(7);  // search + row loads (emit time is folded into 3 in this build)
+#endif
+                    touch2(P, sr, touched, next, sh, v, pf, eps, lane, lt, e0 + T < total PROF_ARGS);
                     PROF_COUNT(8, 1);
                 }
                 PROF(3);  // edge loop (this thread)
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             }
         }
         __syncthreads();
-        PROF(7);  // emit
+        PROF(3);  // emit (counted with the appends)
     }
 #ifdef ARCTE_FRONTIER_PROFILE
     if (tid == 0)
