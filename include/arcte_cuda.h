@@ -233,6 +233,26 @@ int arcte_cuda_community_weighting(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t 
                                    const double *host_weights, int64_t *host_out_indptr, int32_t *host_out_indices,
                                    double *host_out_data, int64_t *out_nnz);
 
+/* The experiment loop (experiments/utility.py:83-104) slices the SAME feature matrix into
+   train/test rows for every fold and weights both blocks.  These calls keep the matrix in HBM:
+   store it once, then per fold gather the two row blocks on the device, compute the chi2 /
+   peak-SNR weights from the training block and weight both blocks; only the weighted blocks
+   travel back.  Results are identical to slicing on the host and calling
+   arcte_cuda_chi2_psnr_weights + arcte_cuda_community_weighting. */
+int arcte_cuda_store_features(arcte_cuda_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *host_indptr,
+                              const int32_t *host_indices, const double *host_data);
+/* The same, adopting the matrix arcte_cuda_assemble (+ arcte_cuda_normalize_features) left on
+   the device: no host round trip between extraction and the experiment loop. */
+int arcte_cuda_store_assembled(arcte_cuda_ctx *ctx);
+/* host_y_*: label matrix of the TRAINING rows, in the order of host_train_rows (n_train x n_classes). */
+int arcte_cuda_weighted_fold(arcte_cuda_ctx *ctx, int64_t n_train, const int64_t *host_train_rows, int64_t n_test,
+                             const int64_t *host_test_rows, int64_t n_classes, const int64_t *host_y_indptr,
+                             const int32_t *host_y_indices, const double *host_y_data, int64_t *train_nnz,
+                             int64_t *test_nnz);
+/* which: 0 = weighted training block, 1 = weighted test block (sizes from arcte_cuda_weighted_fold). */
+int arcte_cuda_get_fold(arcte_cuda_ctx *ctx, int which, int64_t *host_indptr, int32_t *host_indices,
+                        double *host_data);
+
 /* -- text I/O of the console script (host only) ------------------------ */
 /* read_adjacency_matrix, datautil/datarw.py:54-120: parses `src<sep>dst<sep>weight` rows
    ('#' comments) with all host threads (n_threads <= 0: every hardware thread), renumbers the

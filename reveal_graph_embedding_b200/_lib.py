@@ -25,6 +25,7 @@ SYMBOLS = [
     "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features",
     "arcte_cuda_normalize_columns", "arcte_cuda_normalize_features", "arcte_cuda_chi2_contingency", "arcte_cuda_peak_snr",
     "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
+    "arcte_cuda_store_features", "arcte_cuda_store_assembled", "arcte_cuda_weighted_fold", "arcte_cuda_get_fold",
     "arcte_cuda_io_read_edge_list", "arcte_cuda_io_edge_list_copy", "arcte_cuda_io_edge_list_free", "arcte_cuda_io_write_features",
     "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
@@ -95,6 +96,10 @@ def load():
         L.arcte_cuda_peak_snr.argtypes = [vp, i64, i64, vp, vp]
         L.arcte_cuda_chi2_psnr_weights.argtypes = [vp, i64, i64, vp, vp, i64, vp, vp, vp, vp]
         L.arcte_cuda_community_weighting.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+        L.arcte_cuda_store_features.argtypes = [vp, i64, i64, vp, vp, vp]
+        L.arcte_cuda_store_assembled.argtypes = [vp]
+        L.arcte_cuda_weighted_fold.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+        L.arcte_cuda_get_fold.argtypes = [vp, i32, vp, vp, vp]
         L.arcte_cuda_io_read_edge_list.argtypes = [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(vp), C.POINTER(i64),
                                                    C.POINTER(i64)]
         L.arcte_cuda_io_edge_list_copy.argtypes = [vp, vp, vp, vp, vp]

@@ -107,6 +107,8 @@ int arcte_cuda_create(arcte_cuda_ctx **out, int device_id)
     ARCTE_CUDA_TRY(cudaEventCreate(&c->ev1));
     ARCTE_CUDA_TRY(cudaEventCreate(&c->tm0));
     ARCTE_CUDA_TRY(cudaEventCreate(&c->tm1));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->pk0));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->pk1));
     *out = c;
     return ARCTE_OK;
 }
@@ -122,11 +124,16 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
                       &c->out_indices, &c->out_data};
     for (DevBuf *b : bufs) dev_free(*b);
     for (DevBuf &b : c->scratch) dev_free(b);
+    DevBuf *fbufs[] = {&c->fs_indptr, &c->fs_indices, &c->fs_data, &c->fg_indptr, &c->fg_indices, &c->fg_data, &c->fg_rows,
+                       &c->fo_indptr[0], &c->fo_indptr[1], &c->fo_indices[0], &c->fo_indices[1], &c->fo_data[0], &c->fo_data[1]};
+    for (DevBuf *b : fbufs) dev_free(*b);
     for (DevBuf &b : c->peer_stage) dev_free(b);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->tm0);
     cudaEventDestroy(c->tm1);
+    cudaEventDestroy(c->pk0);
+    cudaEventDestroy(c->pk1);
     dev_free(c->l2_flush);
     cudaStreamDestroy(c->stream);
     delete c;

@@ -89,6 +89,7 @@ struct arcte_cuda_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // caller-visible step timer
+    cudaEvent_t pk0 = nullptr, pk1 = nullptr;  // around the push-kernel launches of one extraction
     arcte::DevBuf l2_flush;
 
     // tuning
@@ -136,6 +137,16 @@ struct arcte_cuda_ctx {
     int64_t out_nnz = 0;
     int64_t out_rows = 0;       // rows of the assembled block (n unless row-sharded)
     bool have_features = false;
+
+    // feature matrix kept resident for the experiment loop (weighting.cu): the stored matrix, the
+    // gathered row block of the fold being processed and the two weighted outputs
+    arcte::DevBuf fs_indptr, fs_indices, fs_data;
+    int64_t fs_rows = 0, fs_cols = 0, fs_nnz = 0;
+    bool fs_valid = false;
+    arcte::DevBuf fg_indptr, fg_indices, fg_data, fg_rows;
+    arcte::DevBuf fo_indptr[2], fo_indices[2], fo_data[2];
+    int64_t fo_rows[2] = {0, 0}, fo_nnz[2] = {0, 0};
+    bool fo_valid = false;
 
     // staging for segment parts that live on other GPUs (kept across calls: cudaMalloc/cudaFree
     // serialise the whole process)

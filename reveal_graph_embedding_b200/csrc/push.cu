@@ -749,9 +749,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.as<int64_t>() + PC_T_START, 0xff, sizeof(int64_t), st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->seg_count.p, 0, sizeof(int32_t) * (size_t)S, st));
-    cudaEvent_t p0, p1;
-    ARCTE_CUDA_TRY(cudaEventCreate(&p0));
-    ARCTE_CUDA_TRY(cudaEventCreate(&p1));
+    const cudaEvent_t p0 = c->pk0, p1 = c->pk1;  // owned by the context: nothing to release on the error paths
     ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
     if (frontier) ARCTE_TRY(frontier_launch(c, P, S, false));
     else ARCTE_TRY(launch_push(c, rule, P));
@@ -841,8 +839,6 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, p0, p1));
         stt.ms_push += ms;
     }
-    cudaEventDestroy(p0);
-    cudaEventDestroy(p1);
 
     if (getenv("ARCTE_CUDA_PROFILE")) {  // per-phase clock sums of instrumented kernel builds
         fprintf(stderr, "[arcte] profile counters:");

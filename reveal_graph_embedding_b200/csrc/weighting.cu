@@ -320,6 +320,91 @@ static int upload(arcte_cuda_ctx *c, DevBuf &b, const void *host, size_t bytes)
     return ARCTE_OK;
 }
 
+// community_weighting for one device-resident CSR: outputs into the given buffers (grown as
+// needed), *kept = entries that survive eliminate_zeros().  weights: one double per column.
+static int community_weighting_device(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                      const int64_t *indptr, const int32_t *indices, const double *data,
+                                      const double *weights, DevBuf &out_indptr, DevBuf &out_indices,
+                                      DevBuf &out_data, int64_t *kept)
+{
+    cudaStream_t st = c->stream;
+    ARCTE_TRY(device_col_hist(c, n_cols, nnz, indices, c->scratch[8]));
+    ARCTE_TRY(dev_reserve(c->scratch[9], sizeof(double) * (size_t)n_cols));
+    k_reinforcement<<<wgrid(n_cols, 256), 256, 0, st>>>(n_cols, c->scratch[8].as<int32_t>(), weights,
+                                                        c->scratch[9].as<double>());
+    ARCTE_TRY(dev_reserve(c->scratch[10], sizeof(int32_t) * (size_t)n_rows));
+    k_weighted_row_counts<<<wgrid(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, indices, data,
+                                                                   c->scratch[9].as<double>(),
+                                                                   c->scratch[10].as<int32_t>());
+    c->stats.launches += 2;
+    ARCTE_TRY(dev_reserve(out_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    ARCTE_TRY(exclusive_scan_i32(c->scratch[10].as<int32_t>(), out_indptr.as<int64_t>(), n_rows, c->scratch[0], st,
+                                 &c->stats.launches));
+    ARCTE_TRY(dev_reserve(out_indices, sizeof(int32_t) * (size_t)nnz));
+    ARCTE_TRY(dev_reserve(out_data, sizeof(double) * (size_t)nnz));
+    k_weighted_row_fill<<<wgrid(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, indices, data,
+                                                                 c->scratch[9].as<double>(), out_indptr.as<int64_t>(),
+                                                                 out_indices.as<int32_t>(), out_data.as<double>());
+    ++c->stats.launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(kept, out_indptr.as<int64_t>() + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    return ARCTE_OK;
+}
+
+// X[rows, :] of a device-resident CSR (experiments/utility.py:94-97) into the context's gather
+// buffers: row lengths -> exclusive scan -> one warp copies each row.
+__global__ void k_gather_lengths(int64_t n, const int64_t *__restrict__ rows, const int64_t *__restrict__ indptr,
+                                 int32_t *__restrict__ len)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) len[i] = (int32_t)(indptr[rows[i] + 1] - indptr[rows[i]]);
+}
+__global__ void k_gather_rows(int64_t n, const int64_t *__restrict__ rows, const int64_t *__restrict__ indptr,
+                              const int32_t *__restrict__ indices, const double *__restrict__ data,
+                              const int64_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices,
+                              double *__restrict__ out_data)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int64_t b = indptr[rows[i]], e = indptr[rows[i] + 1], o = out_indptr[i];
+    for (int64_t k = b + lane_id(); k < e; k += 32) {
+        out_indices[o + (k - b)] = indices[k];
+        out_data[o + (k - b)] = data[k];
+    }
+}
+static int gather_rows_device(arcte_cuda_ctx *c, int64_t n, const int64_t *host_rows, const int64_t *indptr,
+                              const int32_t *indices, const double *data, int64_t *nnz_out)
+{
+    cudaStream_t st = c->stream;
+    *nnz_out = 0;
+    ARCTE_TRY(dev_reserve(c->fg_indptr, sizeof(int64_t) * (size_t)(n + 1)));
+    if (n == 0) {
+        ARCTE_CUDA_TRY(cudaMemsetAsync(c->fg_indptr.p, 0, sizeof(int64_t), st));
+        return ARCTE_OK;
+    }
+    ARCTE_TRY(upload(c, c->fg_rows, host_rows, sizeof(int64_t) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->scratch[10], sizeof(int32_t) * (size_t)n));
+    k_gather_lengths<<<wgrid(n, 256), 256, 0, st>>>(n, c->fg_rows.as<int64_t>(), indptr, c->scratch[10].as<int32_t>());
+    ++c->stats.launches;
+    ARCTE_TRY(exclusive_scan_i32(c->scratch[10].as<int32_t>(), c->fg_indptr.as<int64_t>(), n, c->scratch[0], st,
+                                 &c->stats.launches));
+    int64_t nnz = 0;
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(&nnz, c->fg_indptr.as<int64_t>() + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    ARCTE_TRY(dev_reserve(c->fg_indices, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    ARCTE_TRY(dev_reserve(c->fg_data, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
+    if (nnz > 0) {
+        k_gather_rows<<<wgrid(n * 32, 256), 256, 0, st>>>(n, c->fg_rows.as<int64_t>(), indptr, indices, data,
+                                                          c->fg_indptr.as<int64_t>(), c->fg_indices.as<int32_t>(),
+                                                          c->fg_data.as<double>());
+        ++c->stats.launches;
+    }
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    *nnz_out = nnz;
+    return ARCTE_OK;
+}
+
 }  // namespace arcte
 
 using namespace arcte;
@@ -474,42 +559,143 @@ int arcte_cuda_community_weighting(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_
     ARCTE_TRY(upload(c, c->scratch[12], host_indices, sizeof(int32_t) * (size_t)nnz));
     ARCTE_TRY(upload(c, c->scratch[13], host_data, sizeof(double) * (size_t)nnz));
     ARCTE_TRY(upload(c, c->scratch[14], host_weights, sizeof(double) * (size_t)n_cols));
-    const int64_t *indptr = c->scratch[11].as<int64_t>();
-    const int32_t *indices = c->scratch[12].as<int32_t>();
-    const double *data = c->scratch[13].as<double>();
-    ARCTE_TRY(device_col_hist(c, n_cols, nnz, indices, c->scratch[8]));
-    ARCTE_TRY(dev_reserve(c->scratch[9], sizeof(double) * (size_t)n_cols));
-    k_reinforcement<<<wgrid(n_cols, 256), 256, 0, st>>>(n_cols, c->scratch[8].as<int32_t>(),
-                                                        c->scratch[14].as<double>(), c->scratch[9].as<double>());
-    ARCTE_TRY(dev_reserve(c->scratch[10], sizeof(int32_t) * (size_t)n_rows));
-    k_weighted_row_counts<<<wgrid(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, indices, data,
-                                                                   c->scratch[9].as<double>(),
-                                                                   c->scratch[10].as<int32_t>());
-    c->stats.launches += 2;
-    ARCTE_TRY(dev_reserve(c->scratch[15], sizeof(int64_t) * (size_t)(n_rows + 1)));
-    ARCTE_TRY(exclusive_scan_i32(c->scratch[10].as<int32_t>(), c->scratch[15].as<int64_t>(), n_rows, c->scratch[0],
-                                 st, &c->stats.launches));
-    ARCTE_TRY(dev_reserve(c->scratch[6], sizeof(int32_t) * (size_t)nnz));
-    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(double) * (size_t)nnz));
-    k_weighted_row_fill<<<wgrid(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, indices, data,
-                                                                 c->scratch[9].as<double>(),
-                                                                 c->scratch[15].as<int64_t>(),
-                                                                 c->scratch[6].as<int32_t>(),
-                                                                 c->scratch[7].as<double>());
-    ++c->stats.launches;
-    ARCTE_CUDA_TRY(cudaGetLastError());
+    int64_t kept = 0;
+    ARCTE_TRY(community_weighting_device(c, n_rows, n_cols, nnz, c->scratch[11].as<int64_t>(),
+                                         c->scratch[12].as<int32_t>(), c->scratch[13].as<double>(),
+                                         c->scratch[14].as<double>(), c->scratch[15], c->scratch[6], c->scratch[7], &kept));
     ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_indptr, c->scratch[15].p, sizeof(int64_t) * (size_t)(n_rows + 1),
                                    cudaMemcpyDeviceToHost, st));
-    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
-    const int64_t kept = host_out_indptr[n_rows];
     if (kept > 0) {
         ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_indices, c->scratch[6].p, sizeof(int32_t) * (size_t)kept,
                                        cudaMemcpyDeviceToHost, st));
         ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_data, c->scratch[7].p, sizeof(double) * (size_t)kept,
                                        cudaMemcpyDeviceToHost, st));
-        ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     *out_nnz = kept;
+    return ARCTE_OK;
+}
+
+// ---- feature matrix resident in HBM across the folds of an experiment --------------------------
+int arcte_cuda_store_features(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_cols, const int64_t *host_indptr,
+                              const int32_t *host_indices, const double *host_data)
+{
+    CHECK_CTX(c);
+    ARCTE_TRY(check_csr_args("store_features", n_rows, n_cols, host_indptr, host_indices));
+    const int64_t nnz = host_indptr[n_rows];
+    if (nnz > 0 && !host_data) { set_error("store_features: null data"); return ARCTE_E_ARG; }
+    c->fs_valid = c->fo_valid = false;
+    ARCTE_TRY(upload(c, c->fs_indptr, host_indptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    ARCTE_TRY(upload(c, c->fs_indices, host_indices, sizeof(int32_t) * (size_t)nnz));
+    ARCTE_TRY(upload(c, c->fs_data, host_data, sizeof(double) * (size_t)nnz));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->fs_rows = n_rows; c->fs_cols = n_cols; c->fs_nnz = nnz;
+    c->fs_valid = true;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_store_assembled(arcte_cuda_ctx *c)
+{
+    CHECK_CTX(c);
+    if (!c->have_features || c->out_rows != c->n) {
+        set_error("store_assembled: no complete feature matrix is resident (call assemble for all rows first)");
+        return ARCTE_E_ARG;
+    }
+    c->fs_valid = c->fo_valid = false;
+    const size_t nnz = (size_t)c->out_nnz;
+    ARCTE_TRY(dev_reserve(c->fs_indptr, sizeof(int64_t) * (size_t)(c->n + 1)));
+    ARCTE_TRY(dev_reserve(c->fs_indices, sizeof(int32_t) * (nnz ? nnz : 1)));
+    ARCTE_TRY(dev_reserve(c->fs_data, sizeof(double) * (nnz ? nnz : 1)));
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->fs_indptr.p, c->out_indptr.p, sizeof(int64_t) * (size_t)(c->n + 1),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    if (nnz) {
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->fs_indices.p, c->out_indices.p, sizeof(int32_t) * nnz, cudaMemcpyDeviceToDevice, c->stream));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->fs_data.p, c->out_data.p, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->fs_rows = c->n; c->fs_cols = 2 * c->n; c->fs_nnz = c->out_nnz;
+    c->fs_valid = true;
+    return ARCTE_OK;
+}
+
+int arcte_cuda_weighted_fold(arcte_cuda_ctx *c, int64_t n_train, const int64_t *host_train_rows, int64_t n_test,
+                             const int64_t *host_test_rows, int64_t n_classes, const int64_t *host_y_indptr,
+                             const int32_t *host_y_indices, const double *host_y_data, int64_t *train_nnz,
+                             int64_t *test_nnz)
+{
+    CHECK_CTX(c);
+    if (!c->fs_valid) { set_error("weighted_fold: no feature matrix stored (store_features / store_assembled)"); return ARCTE_E_ARG; }
+    if (n_train < 0 || n_test < 0 || n_classes <= 0 || (n_train > 0 && !host_train_rows) ||
+        (n_test > 0 && !host_test_rows) || !host_y_indptr) {
+        set_error("weighted_fold: bad arguments");
+        return ARCTE_E_ARG;
+    }
+    for (int64_t i = 0; i < n_train; ++i)
+        if (host_train_rows[i] < 0 || host_train_rows[i] >= c->fs_rows) { set_error("weighted_fold: training row out of range"); return ARCTE_E_ARG; }
+    for (int64_t i = 0; i < n_test; ++i)
+        if (host_test_rows[i] < 0 || host_test_rows[i] >= c->fs_rows) { set_error("weighted_fold: test row out of range"); return ARCTE_E_ARG; }
+    ARCTE_TRY(check_csr_args("weighted_fold: Y", n_train, n_classes, host_y_indptr, host_y_indices));
+    if (host_y_indptr[n_train] > 0 && !host_y_data) { set_error("weighted_fold: null label data"); return ARCTE_E_ARG; }
+    cudaStream_t st = c->stream;
+    c->stats.launches = 0;
+    c->fo_valid = false;
+    const int64_t F = c->fs_cols;
+    const int64_t *fsp = c->fs_indptr.as<int64_t>();
+    const int32_t *fsi = c->fs_indices.as<int32_t>();
+    const double *fsd = c->fs_data.as<double>();
+    // ---- training block: gather, chi2 + peak SNR weights (kept on the device), weighting ----
+    int64_t g_nnz = 0;
+    ARCTE_TRY(gather_rows_device(c, n_train, host_train_rows, fsp, fsi, fsd, &g_nnz));
+    ARCTE_TRY(upload(c, c->scratch[13], host_y_indptr, sizeof(int64_t) * (size_t)(n_train + 1)));
+    ARCTE_TRY(upload(c, c->scratch[14], host_y_indices, sizeof(int32_t) * (size_t)host_y_indptr[n_train]));
+    ARCTE_TRY(upload(c, c->scratch[15], host_y_data, sizeof(double) * (size_t)host_y_indptr[n_train]));
+    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(double) * (size_t)n_classes * (size_t)(F > 0 ? F : 1)));
+    ARCTE_TRY(dev_reserve(c->scratch[6], sizeof(double) * (size_t)(F > 0 ? F : 1)));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->scratch[6].p, 0, sizeof(double) * (size_t)(F > 0 ? F : 1), st));
+    if (F > 0) {
+        ARCTE_TRY(chi2_device(c, n_train, F, c->fg_indptr.as<int64_t>(), c->fg_indices.as<int32_t>(), n_classes,
+                              c->scratch[13].as<int64_t>(), c->scratch[14].as<int32_t>(), c->scratch[15].as<double>(),
+                              c->scratch[7].as<double>()));
+        ARCTE_TRY(peak_snr_device(c, n_classes, F, c->scratch[7].as<double>(), c->scratch[6].as<double>()));
+    }
+    for (int which = 0; which < 2; ++which) {
+        const int64_t rows = which == 0 ? n_train : n_test;
+        if (which == 1) ARCTE_TRY(gather_rows_device(c, n_test, host_test_rows, fsp, fsi, fsd, &g_nnz));
+        int64_t kept = 0;
+        ARCTE_TRY(dev_reserve(c->fo_indptr[which], sizeof(int64_t) * (size_t)(rows + 1)));
+        if (rows == 0 || g_nnz == 0) {
+            ARCTE_CUDA_TRY(cudaMemsetAsync(c->fo_indptr[which].p, 0, sizeof(int64_t) * (size_t)(rows + 1), st));
+        } else {
+            ARCTE_TRY(community_weighting_device(c, rows, F, g_nnz, c->fg_indptr.as<int64_t>(),
+                                                 c->fg_indices.as<int32_t>(), c->fg_data.as<double>(),
+                                                 c->scratch[6].as<double>(), c->fo_indptr[which], c->fo_indices[which],
+                                                 c->fo_data[which], &kept));
+        }
+        c->fo_rows[which] = rows;
+        c->fo_nnz[which] = kept;
+    }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    c->fo_valid = true;
+    if (train_nnz) *train_nnz = c->fo_nnz[0];
+    if (test_nnz) *test_nnz = c->fo_nnz[1];
+    return ARCTE_OK;
+}
+
+int arcte_cuda_get_fold(arcte_cuda_ctx *c, int which, int64_t *host_indptr, int32_t *host_indices, double *host_data)
+{
+    CHECK_CTX(c);
+    if (!c->fo_valid || which < 0 || which > 1 || !host_indptr) { set_error("get_fold: call weighted_fold first"); return ARCTE_E_ARG; }
+    const int64_t rows = c->fo_rows[which], nnz = c->fo_nnz[which];
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->fo_indptr[which].p, sizeof(int64_t) * (size_t)(rows + 1),
+                                   cudaMemcpyDeviceToHost, c->stream));
+    if (nnz > 0) {
+        if (!host_indices || !host_data) { set_error("get_fold: null output"); return ARCTE_E_ARG; }
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indices, c->fo_indices[which].p, sizeof(int32_t) * (size_t)nnz,
+                                       cudaMemcpyDeviceToHost, c->stream));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_data, c->fo_data[which].p, sizeof(double) * (size_t)nnz,
+                                       cudaMemcpyDeviceToHost, c->stream));
+    }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;
 }
 

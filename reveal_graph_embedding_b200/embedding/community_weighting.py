@@ -56,3 +56,29 @@ def chi2_psnr_community_weighting(X_train, X_test, y_train):
         community_weights = get_engine(0).chi2_psnr_weights(X_train, _label_matrix(y_train))
         X_train, X_test = community_weighting(X_train, X_test, community_weights)
     return X_train, X_test
+
+
+class ResidentFeatures:
+    """The feature matrix kept in HBM across the folds of an experiment.  Per fold,
+
+        X_train, X_test = resident.chi2_psnr_community_weighting(train, test, y_train)
+
+    replaces the reference's (experiments/utility.py:94-104)
+
+        X_train, X_test = feature_matrix[train, :], feature_matrix[test, :]
+        contingency_matrix = chi2_contingency_matrix(X_train, y_train)
+        community_weights = peak_snr_weight_aggregation(contingency_matrix)
+        X_train, X_test = community_weighting(X_train, X_test, community_weights)
+
+    with the row gather, the contingency matrix and the weighting on the device; only the two
+    weighted blocks are copied back.  `feature_matrix=None` adopts the matrix the last
+    arcte() + Engine.normalize_features() left on the device.
+    """
+
+    def __init__(self, feature_matrix=None, device=0):
+        self._eng = get_engine(device)
+        self._eng.store_features(feature_matrix)
+        self.shape = self._eng.stored_shape
+
+    def chi2_psnr_community_weighting(self, train, test, y_train):
+        return self._eng.weighted_fold(train, test, _label_matrix(y_train))

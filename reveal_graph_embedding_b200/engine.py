@@ -336,6 +336,45 @@ class Engine:
         return sparse.csr_matrix((out_data[:k], out_indices[:k].astype(idx_t, copy=False), out_indptr.astype(idx_t)),
                                  shape=shape)
 
+    # -- feature matrix resident across the folds of an experiment ---------------------------------
+    def store_features(self, features=None):
+        """Keep `features` (any scipy sparse matrix) in HBM for weighted_fold(); None adopts the
+        matrix the last assemble() (+ normalize_features()) left on the device."""
+        if features is None:
+            check(self._L.arcte_cuda_store_assembled(self._h))
+            self.stored_shape = (self.n, 2 * self.n)
+            return
+        shape, indptr, indices, data = self._csr_arrays(features)
+        check(self._L.arcte_cuda_store_features(self._h, shape[0], shape[1], ptr(indptr),
+                                                ptr(indices) if data.size else None, ptr(data) if data.size else None))
+        self.stored_shape = shape
+
+    def weighted_fold(self, train, test, Y_train):
+        """X[train], X[test] of the stored matrix, weighted by the chi2 / peak-SNR weights of the
+        training block (utility.py:94-104), everything on the device.  Y_train: binarised labels of
+        the training rows.  Returns (X_train_weighted, X_test_weighted) as scipy CSR."""
+        train = np.ascontiguousarray(train, dtype=np.int64)
+        test = np.ascontiguousarray(test, dtype=np.int64)
+        yshape, y_indptr, y_indices, y_data = self._csr_arrays(Y_train)
+        if yshape[0] != train.size:
+            raise ValueError("one label row per training row is required")
+        a, b = C.c_int64(), C.c_int64()
+        check(self._L.arcte_cuda_weighted_fold(self._h, train.size, ptr(train) if train.size else None, test.size,
+                                               ptr(test) if test.size else None, yshape[1], ptr(y_indptr),
+                                               ptr(y_indices) if y_indices.size else None,
+                                               ptr(y_data) if y_data.size else None, C.byref(a), C.byref(b)))
+        out = []
+        for which, rows, nnz in ((0, train.size, a.value), (1, test.size, b.value)):
+            indptr = np.zeros(rows + 1, dtype=np.int64)
+            indices = hostmem.empty(max(nnz, 1), np.int32)
+            data = hostmem.empty(max(nnz, 1), np.float64)
+            check(self._L.arcte_cuda_get_fold(self._h, which, ptr(indptr), ptr(indices), ptr(data)))
+            idx_t = np.int32 if max(self.stored_shape[1], nnz) < 2 ** 31 else np.int64
+            out.append(sparse.csr_matrix((data[:nnz], indices[:nnz].astype(idx_t, copy=False), indptr.astype(idx_t)),
+                                         shape=(rows, self.stored_shape[1])))
+        hostmem.start_pending()
+        return out[0], out[1]
+
     def timer_start(self):
         check(self._L.arcte_cuda_timer_start(self._h))
 

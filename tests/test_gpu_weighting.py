@@ -185,3 +185,48 @@ def test_downstream_f1_equals_reference(fixtures):
         truth = y_test.toarray()
         assert f1_score(truth, pred, average="macro") == pytest.approx(float(z["t%d_macro_f1" % k]), abs=1e-12)
         assert f1_score(truth, pred, average="micro") == pytest.approx(float(z["t%d_micro_f1" % k]), abs=1e-12)
+
+
+def test_resident_fold_equals_host_sliced_chain(fixtures, wo):
+    """ResidentFeatures (row gather + chi2/PSNR + weighting on the device) == slicing on the host and
+    calling the reference-shaped functions, for the fixture folds and for a larger matrix."""
+    from reveal_graph_embedding_b200 import graphs
+    from reveal_graph_embedding_b200.embedding.arcte.arcte import arcte
+    from reveal_graph_embedding_b200.embedding.common import normalize_columns
+    from reveal_graph_embedding_b200.embedding.community_weighting import (ResidentFeatures,
+                                                                            chi2_psnr_community_weighting)
+    from reveal_graph_embedding_b200.engine import get_engine
+    z, _ = fixtures
+    X = load_npz_csr(z, "X")
+    Xn = sparse.csr_matrix((z["Xn_data"], X.indices, X.indptr), shape=X.shape)
+    Y = load_npz_csr(z, "Y")
+    res = ResidentFeatures(Xn)
+    for k in range(2):
+        tr, te = z["t%d_train" % k], z["t%d_test" % k]
+        a, b = res.chi2_psnr_community_weighting(tr, te, Y[tr, :])
+        for got, name in ((a, "_Xtr"), (b, "_Xte")):
+            want = load_npz_csr(z, "t%d" % k + name)
+            assert got.shape == want.shape
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            assert ulp_diff(got.data, want.data).max() <= ROW_NORM_ULP
+    # larger, unsorted fold indices, features adopted straight from the device
+    A = graphs.barabasi_albert(8000, 3, seed=4)
+    Xh = normalize_columns(arcte(A, RHO, EPS, 1))
+    eng = get_engine(0)
+    eng.set_graph(A)
+    eng.extract(0, RHO, EPS)
+    eng.assemble()
+    eng.normalize_features()
+    res = ResidentFeatures(None)
+    rng = np.random.default_rng(8)
+    n, K = A.shape[0], 9
+    Yb = sparse.csr_matrix((rng.random((n, K)) < 0.2).astype(np.int64))
+    perm = rng.permutation(n)
+    tr, te = perm[:700], perm[700:5000]                      # not sorted, not covering every row
+    a, b = res.chi2_psnr_community_weighting(tr, te, Yb[tr, :])
+    a0, b0 = chi2_psnr_community_weighting(Xh[tr, :], Xh[te, :], Yb[tr, :])
+    assert_csr_identical(a, a0)
+    assert_csr_identical(b, b0)
+    # empty test block
+    a, b = res.chi2_psnr_community_weighting(tr, np.zeros(0, dtype=np.int64), Yb[tr, :])
+    assert_csr_identical(a, a0) and b.shape == (0, 2 * n) and b.nnz == 0

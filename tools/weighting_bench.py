@@ -93,6 +93,15 @@ dev, wall, Xw = timed(lambda: eng.community_weighting(X_test, w), reps=2)
 out["community_weighting_test_block"] = {"device_ms": round(dev, 2), "wall_ms": round(wall, 1), "nnz_in": int(X_test.nnz),
                                          "nnz_out": int(Xw.nnz)}
 
+# ---- the same fold with the matrix resident in HBM: gather + chi2/PSNR + weighting on the device ----
+eng.store_features(Xn)
+def fold():
+    return eng.weighted_fold(train, test, Yb)
+dev, wall, (Ra, Rb) = timed(fold, reps=2)
+out["resident_fold"] = {"device_ms_incl_d2h": round(dev, 2), "wall_ms": round(wall, 1),
+                        "d2h_bytes": int(12 * (Ra.nnz + Rb.nnz)),
+                        "equals_host_sliced_path": bool(np.array_equal(Rb.indices, Xw.indices) and np.array_equal(Rb.data, Xw.data))}
+
 # ---- the CPU oracle port beside it (single thread, same inputs) ----
 if "--no-cpu" not in sys.argv:
     from oracle import weighting_oracle as wo
