@@ -30,6 +30,12 @@
 #include "common.cuh"
 #include "push.cuh"
 
+// Timing experiments only (results are WRONG when a bit is set): 1 = no list appends, 2 = no
+// in-degree gather / threshold test, 4 = no state access, 8 = no binary search (edge e reads CSR
+// position e), 16 = no CSR reads.
+#ifndef ARCTE_FRONTIER_ABLATE
+#define ARCTE_FRONTIER_ABLATE 0
+#endif
 #ifndef ARCTE_FRONTIER_PRELOAD
 #define ARCTE_FRONTIER_PRELOAD 0
 #endif
@@ -64,7 +70,7 @@ __device__ __forceinline__ bool over_threshold(unsigned long long r, double d_in
 }
 
 template <int T> struct WalkShared {
-    int cur_n, next_n, nt, m;
+    int cur_n, next_n, nt, m, dummy;
     long long work;
     long long off;
     unsigned long long edges;
@@ -108,9 +114,17 @@ __device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (pf[k]) {
+#if ARCTE_FRONTIER_ABLATE & 4
+            old_s[k] = 1ull; old_r[k] = add[k];
+#else
             old_s[k] = atomicAdd(&sr[2 * (int64_t)v[k]], add[k]);
             old_r[k] = atomicAdd(&sr[2 * (int64_t)v[k] + 1], add[k]);
+#endif
+#if ARCTE_FRONTIER_ABLATE & 2
+            d[k] = 1.0e30;
+#else
             d[k] = P.info[v[k]].d_in;
+#endif
         }
     }
 #ifdef ARCTE_FRONTIER_PROFILE
@@ -128,12 +142,24 @@ __device__ __forceinline__ void touch2(const PushParams &P, unsigned long long *
                 cross = over_threshold(old_r[k] + pf[k], d[k], eps, P.inv_scale) &&
                         !over_threshold(old_r[k], d[k], eps, P.inv_scale);
         }
+#if ARCTE_FRONTIER_ABLATE & 1
+        if (is_new && v[k] == -7) touched[0] = v[k];
+        if (cross && v[k] == -7) next[0] = v[k];
+        continue;
+#endif
         const unsigned m_new = __ballot_sync(kFull, is_new);
         if (m_new) {
             int base = 0;
             if (lane == __ffs(m_new) - 1) base = atomicAdd(&sh.nt, __popc(m_new));
+#if ARCTE_FRONTIER_ABLATE & 64   // sensitivity test: every append pays a second shared atomic
+            if (lane == __ffs(m_new) - 1) base += atomicAdd(&sh.dummy, 0);
+#endif
             base = __shfl_sync(kFull, base, __ffs(m_new) - 1);
+#if ARCTE_FRONTIER_ABLATE & 128
+            if (is_new && base < 0) touched[0] = v[k];
+#else
             if (is_new) touched[base + __popc(m_new & lt)] = v[k];
+#endif
         }
         const unsigned m_x = __ballot_sync(kFull, cross);
         if (m_x) {
@@ -183,6 +209,7 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
             sh.cur_n = 1;
             sh.next_n = 0;
             sh.edges = 0ull;
+            sh.dummy = 0;
         }
         __syncthreads();
         int32_t *cur = fa, *next = fb;
@@ -252,13 +279,23 @@ __global__ void __launch_bounds__(T) k_push_frontier(const PushParams P)
                         pf[k2] = 0ull;
                         if (e < total) {
                             int lo = 0, hi = T - 1;  // largest entry with eoff <= e
+#if ARCTE_FRONTIER_ABLATE & 8
+                            lo = (int)(e % (unsigned)T);
+                            const unsigned j = sh.ebeg[0] + e;
+#else
                             while (lo < hi) {
                                 const int mid = (lo + hi + 1) >> 1;
                                 if (sh.eoff[mid] <= e) lo = mid; else hi = mid - 1;
                             }
                             const unsigned j = sh.ebeg[lo] + (e - sh.eoff[lo]);
+#endif
+#if ARCTE_FRONTIER_ABLATE & 16
+                            v[k2] = (int)((j * 2654435761u) % (unsigned)P.n);
+                            pf[k2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(sh.ec[lo], 1e-3), P.scale));
+#else
                             v[k2] = P.indices[j];
                             pf[k2] = (unsigned long long)__double2ll_rn(__dmul_rn(__dmul_rn(sh.ec[lo], P.w[j]), P.scale));
+#endif
                         }
                     }
 #ifdef ARCTE_FRONTIER_PROFILE
