@@ -190,10 +190,17 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
     n = eng.n
     # device -> host into pooled page-locked buffers
     h_indices = hostmem.empty(max(total, 1), np.int32)
-    h_data = hostmem.empty(max(total, 1), np.float64)
     torch.from_numpy(h_indices).copy_(indices)
-    torch.from_numpy(h_data).copy_(data)
     h_indptr = indptr.cpu().numpy()
+    # values: ones pre-filled on the host + self-loop diagonals patched, else a device-to-host copy
+    h_data = hostmem.ones(max(total, 1))
+    if h_data is not None:
+        rows, rank_in_row = eng.self_loop_rows()
+        if rows.size:
+            h_data[h_indptr[rows].astype(np.int64) + rank_in_row] = 2.0
+    else:
+        h_data = hostmem.empty(max(total, 1), np.float64)
+        torch.from_numpy(h_data).copy_(data)
     hostmem.start_pending()
     h_indices, h_data = h_indices[:total], h_data[:total]
     if max(2 * n, total) < 2 ** 31:

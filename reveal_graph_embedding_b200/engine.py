@@ -64,6 +64,8 @@ class Engine:
         self.device = int(device)
         self.n = 0
         self.nnz = 0
+        self._loops = None
+        self._values_structural = False
         self.schedule = SCHEDULE_FIFO
 
     def close(self):
@@ -97,6 +99,7 @@ class Engine:
         """Upload the adjacency CSR and build the transition matrix (K1) and seed list (K2a)."""
         A = adjacency_matrix if canonical else canonical_csr(adjacency_matrix)
         self.n, self.nnz = int(A.shape[0]), int(A.nnz)
+        self._loops = None
         self._indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         self._indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         self._data = np.ascontiguousarray(A.data, dtype=np.float64)
@@ -105,6 +108,7 @@ class Engine:
 
     def set_transition(self, indptr, indices, w, d_out, d_in):
         """Upload W, out_degree, in_degree as given (arcte_worker's raw arrays, arcte.py:279-286)."""
+        self._loops = None
         self._indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         self._indices = np.ascontiguousarray(indices, dtype=np.int32)
         self._data = np.ascontiguousarray(w, dtype=np.float64)
@@ -205,6 +209,8 @@ class Engine:
                                                    ptr(cols[2]), ptr(cols[3]), int(row_lo), row_hi, C.byref(nnz)))
         self.out_nnz = nnz.value
         self.out_rows = row_hi - int(row_lo)
+        self.out_row_lo = int(row_lo)
+        self._values_structural = True
         return nnz.value
 
     def features_device(self):
@@ -230,9 +236,9 @@ class Engine:
         rows = getattr(self, "out_rows", self.n)
         assert indptr.dtype == np.int64 and indptr.size == rows + 1 and indptr.flags.c_contiguous
         assert indices.dtype == np.int32 and indices.size == self.out_nnz and indices.flags.c_contiguous
-        assert data.dtype == np.float64 and data.size == self.out_nnz and data.flags.c_contiguous
+        assert data is None or (data.dtype == np.float64 and data.size == self.out_nnz and data.flags.c_contiguous)
         check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices) if self.out_nnz else None,
-                                              ptr(data) if self.out_nnz else None))
+                                              ptr(data) if (self.out_nnz and data is not None) else None))
 
     def features(self):
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
@@ -241,8 +247,11 @@ class Engine:
             raise ArcteCudaError("features(): only a row block is assembled; use the distributed path")
         indptr = np.empty(self.n + 1, dtype=np.int64)
         indices = hostmem.empty(max(nnz, 1), np.int32)   # page-locked for large results
-        data = hostmem.empty(max(nnz, 1), np.float64)
-        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), ptr(data)))
+        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), None))
+        data = self.structural_values(indptr)            # ones pre-filled on the host: no copy of the values
+        if data is None:
+            data = hostmem.empty(max(nnz, 1), np.float64)
+            check(self._L.arcte_cuda_get_features(self._h, None, None, ptr(data)))
         hostmem.start_pending()
         indices = indices[:nnz]
         data = data[:nnz]
@@ -280,6 +289,37 @@ class Engine:
     def normalize_features(self):
         """normalize_columns on the assembled feature matrix resident on the device, in place."""
         check(self._L.arcte_cuda_normalize_features(self._h))
+        self._values_structural = False
+
+    def self_loop_rows(self):
+        """(rows, rank): rows whose diagonal entry is stored in the uploaded matrix (their identity
+        entry is 2.0) and the number of stored entries before it in the row."""
+        if self._loops is None:
+            ip, ix = self._indptr, self._indices
+            rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(ip))
+            k = np.flatnonzero(ix == rows) if ix.size else np.zeros(0, dtype=np.int64)
+            self._loops = (rows[k], k - ip[rows[k]])
+        return self._loops
+
+    def structural_values(self, out_indptr, row_lo=0, row_hi=None):
+        """The value array of the assembled block rows [row_lo, row_hi) WITHOUT copying it from the
+        device: every stored value is 1.0 (arcte.py:379-381, :676-679) except the identity entry of
+        a row with a self loop, which is 2.0.  Returns a page-locked array of ones with those entries
+        patched, or None when no pre-filled block is ready / the values were changed on the device
+        (normalize_features); the caller then copies the values as usual.  out_indptr: the block's
+        row pointers (starting at 0)."""
+        if not self._values_structural:
+            return None
+        nnz = int(out_indptr[-1])
+        data = hostmem.ones(max(nnz, 1))
+        if data is None:
+            return None
+        row_hi = self.n if row_hi is None else row_hi
+        rows, rank = self.self_loop_rows()
+        m = (rows >= row_lo) & (rows < row_hi)
+        if m.any():   # the diagonal is the rank-th base-block column of its row (columns < n come first)
+            data[np.asarray(out_indptr)[rows[m] - row_lo].astype(np.int64) + rank[m]] = 2.0
+        return data
 
     def chi2_contingency(self, X_train, Y):
         """embedding/community_weighting.py:11-45; Y = binarised label matrix (sparse)."""

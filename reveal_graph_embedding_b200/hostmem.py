@@ -89,12 +89,90 @@ def empty(count, dtype):
     return np.frombuffer(buf, dtype=dtype, count=int(count))
 
 
+# ---- blocks pre-filled with 1.0 -----------------------------------------------------------------
+# Every stored value of an ARCTE feature matrix is 1.0 except the diagonal entries of self loops
+# (arcte.py:676-679: I + pattern(A); local block np.ones_like, arcte.py:379-381), and the values
+# are two thirds of the bytes of the result.  A pooled page-locked block that already holds
+# ones lets the caller skip the device-to-host copy of the values altogether (the few 2.0
+# entries are patched on the host).  A block that comes back from a caller may have been
+# modified, so it is refilled in the background before it is offered again.
+_ones_free = []      # [(bytes, address)]
+_pending_ones = []
+counters = {"ones_hits": 0, "ones_misses": 0}
+
+
+def _fill_ones(addr, nbytes):
+    buf = (C.c_char * nbytes).from_address(addr)
+    a = np.frombuffer(buf, dtype=np.float64, count=nbytes // 8)
+    step = 1 << 24
+    for i in range(0, a.size, step):   # in slices: keeps the GIL hand-over frequent
+        a[i:i + step] = 1.0
+
+
+def _release_ones(addr, nbytes):
+    t = threading.Thread(target=_refill_and_pool, args=(addr, nbytes), daemon=True)
+    t.start()
+    _threads.append(t)
+
+
+def _refill_and_pool(addr, nbytes):
+    global _pooled_bytes
+    _fill_ones(addr, nbytes)
+    with _lock:
+        if _pooled_bytes + nbytes <= _POOL_LIMIT_BYTES:
+            _ones_free.append((nbytes, addr))
+            _pooled_bytes += nbytes
+            return
+    _lib.load().arcte_cuda_host_free(C.c_void_p(addr))
+
+
+def _make_ones(nbytes):
+    with _lock:
+        if _pooled_bytes + nbytes > _POOL_LIMIT_BYTES:
+            return
+    p = C.c_void_p()
+    if _lib.load().arcte_cuda_host_alloc(C.byref(p), int(nbytes)) != 0:
+        return
+    _refill_and_pool(p.value, nbytes)
+
+
+def ones(count):
+    """A float64 array of `count` ones in a pooled page-locked block, or None when no such block
+    is ready (one is then prepared in the background for the next call)."""
+    global _pooled_bytes
+    nbytes = int(count) * 8
+    if not enabled() or nbytes < _MIN_PINNED_BYTES or os.environ.get("ARCTE_CUDA_ONES_POOL", "1") == "0":
+        return None
+    with _lock:
+        best = None
+        for i, (b, a) in enumerate(_ones_free):
+            if b >= nbytes and b <= nbytes + (nbytes >> 2) + 4096 and (best is None or b < _ones_free[best][0]):
+                best = i
+        if best is not None:
+            block, addr = _ones_free.pop(best)
+            _pooled_bytes -= block
+        else:
+            addr = None
+    if addr is None:
+        _pending_ones.append(nbytes)
+        counters["ones_misses"] += 1
+        return None
+    counters["ones_hits"] += 1
+    buf = (C.c_char * block).from_address(addr)
+    weakref.finalize(buf, _release_ones, addr, block)
+    return np.frombuffer(buf, dtype=np.float64, count=int(count))
+
+
 def start_pending():
     """Start page-locking blocks for the sizes that missed the pool (called after the
     device-to-host copy that used the pageable fallback has finished, so the two do not
     compete for the host's memory system)."""
     while _pending:
         t = threading.Thread(target=_prepin, args=(_pending.pop(),), daemon=True)
+        t.start()
+        _threads.append(t)
+    while _pending_ones:
+        t = threading.Thread(target=_make_ones, args=(_pending_ones.pop(),), daemon=True)
         t.start()
         _threads.append(t)
 
@@ -109,8 +187,9 @@ def drain():
     """Free every pooled block (tests)."""
     global _pooled_bytes
     with _lock:
-        blocks = list(_free)
+        blocks = list(_free) + list(_ones_free)
         _free.clear()
+        _ones_free.clear()
         _pooled_bytes = 0
     for _, a in blocks:
         _lib.load().arcte_cuda_host_free(C.c_void_p(a))
