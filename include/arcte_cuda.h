@@ -278,6 +278,10 @@ int arcte_cuda_io_write_features(const char *path, const char *separator, int64_
    driver's staging buffer.  Not tied to a context. */
 int arcte_cuda_host_alloc(void **out, int64_t bytes);
 int arcte_cuda_host_free(void *p);
+/* Fills count doubles with `value` using n_threads host threads (<= 0: all).  Every stored value
+   of a feature matrix is 1.0 except self-loop diagonals (arcte.py:379-381, :676-679), so a pooled
+   page-locked block that already holds ones saves the device-to-host copy of the value array. */
+int arcte_cuda_host_fill_f64(double *p, int64_t count, double value, int n_threads);
 
 /* -- measurement helpers ------------------------------------------------------ */
 /* CUDA events on the context's own stream (the stream every kernel of this library is

@@ -27,7 +27,7 @@ SYMBOLS = [
     "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
     "arcte_cuda_store_features", "arcte_cuda_store_assembled", "arcte_cuda_weighted_fold", "arcte_cuda_get_fold",
     "arcte_cuda_io_read_edge_list", "arcte_cuda_io_edge_list_copy", "arcte_cuda_io_edge_list_free", "arcte_cuda_io_write_features",
-    "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
+    "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_host_fill_f64", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
         L.arcte_cuda_io_write_features.argtypes = [C.c_char_p, C.c_char_p, i64, vp, vp, vp, vp, i32, C.POINTER(i64)]
         L.arcte_cuda_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.arcte_cuda_host_free.argtypes = [vp]
+        L.arcte_cuda_host_fill_f64.argtypes = [vp, i64, dbl, i32]
         L.arcte_cuda_timer_start.argtypes = [vp]
         L.arcte_cuda_timer_stop.argtypes = [vp, C.POINTER(dbl)]
         L.arcte_cuda_flush_l2.argtypes = [vp]

@@ -401,4 +401,22 @@ int arcte_cuda_io_write_features(const char *path, const char *separator, int64_
     return ARCTE_OK;
 }
 
+
+// Fills count doubles with `value` using all host threads (hostmem.py keeps pooled page-locked
+// blocks pre-filled with 1.0 so that the value array of a feature matrix need not be copied).
+int arcte_cuda_host_fill_f64(double *p, int64_t count, double value, int n_threads)
+{
+    if (!p || count < 0) { set_error("host_fill: bad arguments"); return ARCTE_E_ARG; }
+    int T = pick_threads(n_threads);
+    if ((int64_t)T > count / (1 << 20) + 1) T = (int)(count / (1 << 20) + 1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([=] {
+            const int64_t b = count / T * t, e = t == T - 1 ? count : count / T * (t + 1);
+            for (int64_t i = b; i < e; ++i) p[i] = value;
+        });
+    for (auto &x : th) x.join();
+    return ARCTE_OK;
+}
+
 }  // extern "C"

@@ -101,12 +101,13 @@ _pending_ones = []
 counters = {"ones_hits": 0, "ones_misses": 0}
 
 
+_ONES_BLOCK_LIMIT = 4   # blocks of ones alive at any time (pooled, handed out or being refilled)
+_ones_alive = [0]
+
+
 def _fill_ones(addr, nbytes):
-    buf = (C.c_char * nbytes).from_address(addr)
-    a = np.frombuffer(buf, dtype=np.float64, count=nbytes // 8)
-    step = 1 << 24
-    for i in range(0, a.size, step):   # in slices: keeps the GIL hand-over frequent
-        a[i:i + step] = 1.0
+    # native, multi-threaded, GIL released (ctypes): a 4 GB block takes a fraction of a second
+    _lib.load().arcte_cuda_host_fill_f64(C.c_void_p(addr), nbytes // 8, 1.0, 0)
 
 
 def _release_ones(addr, nbytes):
@@ -123,15 +124,19 @@ def _refill_and_pool(addr, nbytes):
             _ones_free.append((nbytes, addr))
             _pooled_bytes += nbytes
             return
+        _ones_alive[0] -= 1
     _lib.load().arcte_cuda_host_free(C.c_void_p(addr))
 
 
 def _make_ones(nbytes):
     with _lock:
-        if _pooled_bytes + nbytes > _POOL_LIMIT_BYTES:
+        if _pooled_bytes + nbytes > _POOL_LIMIT_BYTES or _ones_alive[0] >= _ONES_BLOCK_LIMIT:
             return
+        _ones_alive[0] += 1
     p = C.c_void_p()
     if _lib.load().arcte_cuda_host_alloc(C.byref(p), int(nbytes)) != 0:
+        with _lock:
+            _ones_alive[0] -= 1
         return
     _refill_and_pool(p.value, nbytes)
 
@@ -154,7 +159,8 @@ def ones(count):
         else:
             addr = None
     if addr is None:
-        _pending_ones.append(nbytes)
+        if _ones_alive[0] + len(_pending_ones) < _ONES_BLOCK_LIMIT:   # else one is being refilled: wait for it
+            _pending_ones.append(nbytes + (nbytes >> 4))               # head-room: results of nearby sizes reuse it
         counters["ones_misses"] += 1
         return None
     counters["ones_hits"] += 1
@@ -188,6 +194,7 @@ def drain():
     global _pooled_bytes
     with _lock:
         blocks = list(_free) + list(_ones_free)
+        _ones_alive[0] -= len(_ones_free)
         _free.clear()
         _ones_free.clear()
         _pooled_bytes = 0
