@@ -85,7 +85,7 @@ def empty(count, dtype):
         _pending.append(nbytes)  # pinned in the background once the caller's copy is done
         return np.empty(int(count), dtype=dtype)
     buf = (C.c_char * block).from_address(addr)
-    weakref.finalize(buf, _release, addr, block)
+    weakref.finalize(buf, _release, addr, block).atexit = False   # nothing to recycle at interpreter exit
     return np.frombuffer(buf, dtype=dtype, count=int(count))
 
 
@@ -165,7 +165,7 @@ def ones(count):
         return None
     counters["ones_hits"] += 1
     buf = (C.c_char * block).from_address(addr)
-    weakref.finalize(buf, _release_ones, addr, block)
+    weakref.finalize(buf, _release_ones, addr, block).atexit = False   # (would start a thread during shutdown)
     return np.frombuffer(buf, dtype=np.float64, count=int(count))
 
 
