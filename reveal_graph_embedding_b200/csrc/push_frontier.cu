@@ -454,19 +454,23 @@ int launch_frontier_kernel(arcte_cuda_ctx *c, const PushParams &P, int threads, 
 
 // Launch geometry: the head of the count-descending seed list (the long walks) can be given
 // fewer, larger CTAs than the rest.  Measured on the YouTube shape the geometry hardly matters
-// (3.9-4.9 s from 296 walks of 512 threads to 2580 walks of 32 threads), so by default every
-// seed is walked by 64 threads, 16 walks per SM (profiles/r1_frontier_schedule.md).
+// (3.9-4.9 s from 296 walks of 512 threads to 2580 walks of 32 threads); on small and medium
+// graphs it does (profiles/r1_frontier_schedule.md), hence the two defaults below.
 struct Geometry {
     int heavy_threads, heavy_ctas, light_threads, light_ctas, heavy_permille;
 };
-Geometry geometry(const arcte_cuda_ctx *c)
+Geometry geometry(const arcte_cuda_ctx *c, int64_t n_work)
 {
     Geometry g;
     g.heavy_permille = c->fr_heavy_permille >= 0 ? c->fr_heavy_permille : 0;
     g.heavy_threads = c->fr_heavy_threads > 0 ? c->fr_heavy_threads : 512;
     g.heavy_ctas = c->fr_heavy_ctas > 0 ? c->fr_heavy_ctas : 2;
-    g.light_threads = c->fr_light_threads > 0 ? c->fr_light_threads : 64;
-    g.light_ctas = c->fr_light_ctas > 0 ? c->fr_light_ctas : 16;
+    // Few seeds (up to a few rounds of the walks in flight): the launch is as long as its longest
+    // walk, so a walk gets 512 threads (BA(5000,5): 1.4 ms against 3.5 ms at 64 threads and 18 ms for
+    // the FIFO).  Many seeds: throughput counts, 64 threads x 16 walks per SM measured best.
+    const bool few = n_work <= 50000;
+    g.light_threads = c->fr_light_threads > 0 ? c->fr_light_threads : (few ? 512 : 64);
+    g.light_ctas = c->fr_light_ctas > 0 ? c->fr_light_ctas : (few ? 2 : 16);
     return g;
 }
 
@@ -484,7 +488,7 @@ double frontier_scale(double rho)
 
 int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots)
 {
-    const Geometry g = geometry(c);
+    const Geometry g = geometry(c, n_work);
     int64_t want = (int64_t)c->sm_count * (g.heavy_ctas > g.light_ctas ? g.heavy_ctas : g.light_ctas);
     if (want > n_work) want = n_work;
     if (want < 1) want = 1;
@@ -539,7 +543,7 @@ int frontier_ensure_slots(arcte_cuda_ctx *c, int64_t want)
 // the light one (a retry pass or a single seed: one launch).
 int frontier_launch(arcte_cuda_ctx *c, PushParams P, int64_t n_work, bool retry_pass)
 {
-    const Geometry g = geometry(c);
+    const Geometry g = geometry(c, n_work);
     P.frontier = c->slots.frontier.as<int32_t>();
     P.fval = c->slots.fval.as<double>();
     const int64_t max_slots = P.n_slots;
