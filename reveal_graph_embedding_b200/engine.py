@@ -45,7 +45,10 @@ def canonical_csr(adjacency_matrix):
     """What the reference feeds its workers: float64 CSR with sorted indices
     (transition.py:52,65).  Duplicate entries are summed (the reference's numpy
     fancy-index `+=` is ill-defined on them)."""
-    A = sparse.csr_matrix(adjacency_matrix, dtype=np.float64)  # no copy if already float64 CSR
+    if sparse.isspmatrix_csr(adjacency_matrix) and adjacency_matrix.dtype == np.float64:
+        A = adjacency_matrix  # as is: scipy caches the canonical-format check on the object
+    else:
+        A = sparse.csr_matrix(adjacency_matrix, dtype=np.float64)
     if A.shape[0] != A.shape[1]:
         raise ValueError("adjacency matrix must be square, got %r" % (A.shape,))
     if not A.has_canonical_format:
