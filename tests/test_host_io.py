@@ -157,3 +157,26 @@ def test_native_writer_rejects_non_finite(tmp_path):
     X = sparse.csr_matrix(np.array([[1.0, np.nan], [0.0, 2.0]]))
     with pytest.raises(ArcteCudaError, match="not a finite"):
         write_features(str(tmp_path / "f.txt"), X, "\t", {0: 5, 1: 6})
+
+
+# ---- host-side input handling (engine.canonical_csr; arcte.py:601 csr_matrix(adjacency_matrix)) ----
+def test_canonical_csr_host_logic():
+    from reveal_graph_embedding_b200.engine import canonical_csr
+    rng = np.random.default_rng(3)
+    A = sparse.random(50, 50, density=0.1, random_state=rng, format="csr")
+    A.sum_duplicates(); A.sort_indices()
+    assert canonical_csr(A) is A                                   # canonical float64 CSR: used as is
+    for conv in (sparse.coo_matrix, sparse.csc_matrix, sparse.lil_matrix, lambda M: M.astype(np.float32)):
+        B = canonical_csr(conv(A))
+        assert sparse.isspmatrix_csr(B) and B.dtype == np.float64 and B.has_canonical_format
+        assert (B != A).nnz == 0 or conv is not sparse.coo_matrix and np.allclose(B.toarray(), A.toarray())
+    # unsorted indices + a duplicate entry: canonicalised on a copy, the caller's arrays untouched
+    rows, cols, vals = [0, 0, 0, 1], [3, 1, 3, 2], [1.0, 2.0, 4.0, 5.0]
+    D = sparse.csr_matrix((np.array(vals), np.array(cols), np.array([0, 3, 4, 4, 4])), shape=(4, 4))
+    before = (D.indices.copy(), D.data.copy(), D.indptr.copy())
+    E = canonical_csr(D)
+    assert E is not D and E.has_canonical_format
+    assert np.array_equal(E.toarray(), np.array([[0, 2.0, 0, 5.0], [0, 0, 5.0, 0], [0] * 4, [0] * 4]))
+    assert all(np.array_equal(a, b) for a, b in zip(before, (D.indices, D.data, D.indptr)))
+    with pytest.raises(ValueError, match="square"):
+        canonical_csr(sparse.csr_matrix((3, 4)))
