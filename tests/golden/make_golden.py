@@ -183,8 +183,13 @@ def main():
         "planted419": (graph_planted(419, 5, 0.35, 0.05, 419), 4, False),
         "edgecases160": (graph_edgecases(5), 8, True),
         "ba2000": (graph_ba(2000, 4, 11), 4, False),
+        # SURVEY.md section 4 known answer: nnz 233,123, local block 178,173, 533,063 pushes
+        "ba5000": (graph_ba(5000, 5, 7), 3, False),
     }
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
     for name, (A, probes, variants) in graphs.items():
+        if only and name not in only:
+            continue
         out = run_reference(A, probes, variants)
         if name == "ba300":
             out.update(pairwise_fixture())
@@ -226,4 +231,5 @@ def cli_fixture():
 if __name__ == "__main__":
     if "--cli-only" not in sys.argv:
         main()
-    cli_fixture()
+    if not [a for a in sys.argv[1:] if not a.startswith("--")]:
+        cli_fixture()

@@ -5,7 +5,7 @@ import numpy as np
 import scipy.sparse as sparse
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_NAMES = ["ba300", "weighted200", "planted419", "edgecases160", "ba2000"]
+GOLDEN_NAMES = ["ba300", "weighted200", "planted419", "edgecases160", "ba2000", "ba5000"]
 RHO, EPS = 0.1, 1e-5
 
 
