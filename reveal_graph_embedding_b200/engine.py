@@ -15,6 +15,10 @@ from ._lib import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, SCHEDULE_FIFO, SCHE
 
 _SCHEDULES = {"fifo": SCHEDULE_FIFO, "exact": SCHEDULE_FIFO, "frontier": SCHEDULE_FRONTIER,
               SCHEDULE_FIFO: SCHEDULE_FIFO, SCHEDULE_FRONTIER: SCHEDULE_FRONTIER}
+# "auto": frontier when a shard has at most this many seeds (the FIFO launch is then as long as its
+# longest walk and the frontier schedule is 2-12x faster, profiles/r1_frontier_schedule.md), FIFO
+# above it and for the PageRank rules.  Never the default: the two schedules differ in tie entries.
+AUTO_FRONTIER_MAX_SEEDS = 40000
 _default_schedule = [None]  # set_default_schedule(); None = ARCTE_CUDA_SCHEDULE or "fifo"
 
 
@@ -23,12 +27,12 @@ def set_default_schedule(schedule):
     the reference's queue, the default) or "frontier" (synchronous fixed-point rounds:
     deterministic, same error bound, support equal up to in-band ties; several times faster).
     The environment variable ARCTE_CUDA_SCHEDULE sets the same default."""
-    if schedule is not None and schedule not in _SCHEDULES:
+    if schedule is not None and schedule != "auto" and schedule not in _SCHEDULES:
         raise ValueError("unknown schedule %r" % (schedule,))
     _default_schedule[0] = schedule
-    for e in _ENGINES.values():
-        if e._h is not None:
-            e.set_schedule(_resolve_schedule())
+    for dev in list(_ENGINES):
+        if _ENGINES[dev]._h is not None:
+            get_engine(dev)
 
 
 def _resolve_schedule():
@@ -36,8 +40,8 @@ def _resolve_schedule():
     name = _default_schedule[0]
     if name is None:
         name = os.environ.get("ARCTE_CUDA_SCHEDULE", "fifo").strip().lower() or "fifo"
-    if name not in _SCHEDULES:
-        raise ValueError("ARCTE_CUDA_SCHEDULE must be 'fifo' or 'frontier', got %r" % (name,))
+    if name != "auto" and name not in _SCHEDULES:
+        raise ValueError("ARCTE_CUDA_SCHEDULE must be 'fifo', 'frontier' or 'auto', got %r" % (name,))
     return name
 
 
@@ -70,6 +74,7 @@ class Engine:
         self._loops = None
         self._values_structural = False
         self.schedule = SCHEDULE_FIFO
+        self.auto_schedule = False
 
     def close(self):
         if getattr(self, "_h", None):
@@ -167,6 +172,14 @@ class Engine:
         ov = None
         if eps_override is not None:
             ov = np.ascontiguousarray(eps_override, dtype=np.float64)
+        if self.auto_schedule:
+            k = C.c_int64()
+            check(self._L.arcte_cuda_get_seed_count(self._h, C.byref(k)))
+            per_shard = -(-k.value // max(int(shard_count), 1))
+            want = (SCHEDULE_FRONTIER if int(rule) == RULE_ABSORBING and per_shard <= AUTO_FRONTIER_MAX_SEEDS
+                    else SCHEDULE_FIFO)
+            if want != self.schedule:
+                self.set_schedule(want)
         ns, nm = C.c_int64(), C.c_int64()
         check(self._L.arcte_cuda_extract(self._h, int(rule), float(rho), float(epsilon), int(shard_rank),
                                          int(shard_count), ptr(ov), C.byref(ns), C.byref(nm)))
@@ -444,9 +457,10 @@ def get_engine(device=0):
     if e is None or e._h is None:
         e = Engine(device)
         _ENGINES[device] = e
-    want = _SCHEDULES[_resolve_schedule()]
-    if e.schedule != want:
-        e.set_schedule(want)
+    name = _resolve_schedule()
+    e.auto_schedule = name == "auto"
+    if not e.auto_schedule and e.schedule != _SCHEDULES[name]:
+        e.set_schedule(_SCHEDULES[name])
     return e
 
 

@@ -244,3 +244,30 @@ def test_gpu_frontier_full_size_sample(oracle):
     gs = e.stats()
     assert gs["pushes"] == st["pushes"] and gs["edge_touches"] == st["edges"] and gs["members"] == st["members"]
     e.close()
+
+
+@pytest.mark.gpu
+def test_auto_schedule_picks_by_seed_count_and_rule(oracle):
+    """ARCTE_CUDA_SCHEDULE=auto / set_default_schedule("auto"): frontier for few seeds and the
+    absorbing rule, FIFO otherwise; the FIFO default is untouched afterwards."""
+    from reveal_graph_embedding_b200 import engine, graphs
+    from reveal_graph_embedding_b200.embedding.arcte.arcte import arcte, arcte_with_pagerank
+    A, z = load_golden("ba2000")
+    try:
+        engine.set_default_schedule("auto")
+        X = arcte(A, RHO, EPS, 1)
+        eng = engine.get_engine(0)
+        assert eng.stats()["rounds"] > 0                       # walked by the frontier schedule
+        g = oracle.Graph(A)
+        with oracle.schedule(oracle.SCHEDULE_FRONTIER):
+            sd, seg, mem, eff, st = oracle.extract(g, 0, RHO, EPS, eng.seeds(), 4)
+            assert_csr_identical(X, oracle.assemble(g, sd, seg, mem))
+        Xp = arcte_with_pagerank(A, RHO, EPS, 1)               # PageRank rule: FIFO under "auto"
+        assert eng.stats()["rounds"] == 0
+        big = graphs.barabasi_albert(50000, 2, seed=3)         # > 40,000 seeds: FIFO
+        arcte(big, RHO, EPS, 1)
+        assert eng.stats()["rounds"] == 0 and eng.stats()["n_seeds_shard"] > engine.AUTO_FRONTIER_MAX_SEEDS
+    finally:
+        engine.set_default_schedule(None)
+    X0 = arcte(A, RHO, EPS, 1)
+    assert_csr_identical(X0, golden_features(z, 0, A.shape[0]))  # back to the exact default
