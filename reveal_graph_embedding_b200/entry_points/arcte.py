@@ -1,43 +1,37 @@
-"""The `arcte` console script with the reference's flags (entry_points/arcte.py:12-84)."""
+"""The `arcte` console script: same flags as the reference's (entry_points/arcte.py:16-45),
+edge list in, feature list out, with the text I/O and the extraction running in the native library."""
 import argparse
 
-import numpy as np
 import scipy.sparse as spsp
 
 from ..embedding.arcte.arcte import arcte
 from ..io import read_adjacency_matrix, write_features
 
+# (short flag, long flag, destination, type, default, required, help): the reference's command line
+_FLAGS = (
+    ("-i", "--input", "input_edge_list_path", str, None, True, "edge list: one `source<sep>target<sep>weight` row per edge"),
+    ("-o", "--output", "output_feature_path", str, None, True, "where the `node<sep>community<sep>value` rows go"),
+    ("-s", "--separator", "separator", str, "\t", False, "field separator of both files (default: tab)"),
+    ("-u", "--undirected", "undirected", bool, False, False, "add the reverse of every listed edge"),
+    ("-r", "--rho", "restart_probability", float, 0.1, False, "restart probability of the absorbing walks (default 0.1)"),
+    ("-e", "--epsilon", "epsilon_threshold", float, 1.0e-05, False, "push threshold epsilon (default 1e-5)"),
+    ("-nt", "--tasks", "number_of_tasks", int, None, False, "GPUs to use (the reference: worker processes); default all"),
+)
+
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument("-i", "--input", dest="input_edge_list_path", type=str, required=True,
-                        help="This is the file path of the graph in edge list format.")
-    parser.add_argument("-o", "--output", dest="output_feature_path", type=str, required=True,
-                        help="This is the file path of the output features.")
-    parser.add_argument("-s", "--separator", dest="separator", type=str, required=False, default="\t",
-                        help="The character(s) separating the values in the edge list (default is tab).")
-    parser.add_argument("-u", "--undirected", dest="undirected", type=bool, required=False, default=False,
-                        help="Also create the reciprocal edge for each edge in edge list.")
-    parser.add_argument("-r", "--rho", dest="restart_probability", type=float, required=False, default=0.1,
-                        help="The restart probability for the vertex-centric PageRank calculation.")
-    parser.add_argument("-e", "--epsilon", dest="epsilon_threshold", type=float, required=False,
-                        default=1.0e-05, help="The tolerance for calculating vertex-centric PageRank values.")
-    parser.add_argument("-nt", "--tasks", dest="number_of_tasks", type=int, required=False, default=None,
-                        help="The number of GPUs to use (the reference: parallel tasks).")
+    parser = argparse.ArgumentParser(description="ARCTE community features of a graph, on B200 GPUs.")
+    for short, long_, dest, typ, default, required, text in _FLAGS:
+        parser.add_argument(short, long_, dest=dest, type=typ, default=default, required=required, help=text)
     args = parser.parse_args(argv)
 
-    adjacency_matrix, node_to_id = read_adjacency_matrix(file_path=args.input_edge_list_path,
-                                                         separator=args.separator,
-                                                         undirected=args.undirected)
-    # entry_points/arcte.py:70-71: make sure the matrix is symmetric
-    adjacency_matrix = spsp.csr_matrix(adjacency_matrix)
-    adjacency_matrix = (adjacency_matrix + adjacency_matrix.transpose()) / 2
-
-    features = arcte(adjacency_matrix=adjacency_matrix, rho=args.restart_probability,
-                     epsilon=args.epsilon_threshold, number_of_threads=args.number_of_tasks)
-    features = spsp.csr_matrix(features)
-    write_features(file_path=args.output_feature_path, features=features, separator=args.separator,
-                   node_to_id=node_to_id)
+    graph, node_to_id = read_adjacency_matrix(file_path=args.input_edge_list_path, separator=args.separator,
+                                              undirected=args.undirected)
+    graph = spsp.csr_matrix(graph)
+    graph = (graph + graph.transpose()) / 2        # entry_points/arcte.py:70-71: symmetrise
+    features = arcte(graph, args.restart_probability, args.epsilon_threshold, args.number_of_tasks)
+    write_features(file_path=args.output_feature_path, features=spsp.csr_matrix(features),
+                   separator=args.separator, node_to_id=node_to_id)
 
 
 if __name__ == "__main__":
