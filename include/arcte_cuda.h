@@ -62,6 +62,19 @@ enum {
                                     launch geometry).  Absorbing rule (arcte) only. */
 };
 
+/* Engines of the exact FIFO schedule (arcte_cuda_set_engine).  All three replay the reference's queue
+   discipline and arithmetic exactly (bit-identical s, r, push counts and supports); they differ in how
+   the walk state is laid out and in how many queue entries one warp iteration takes. */
+enum {
+    ARCTE_ENGINE_AUTO = -1,          /* absorbing rule: BATCHED_HASH when n > 2^18, else BATCHED_DENSE;
+                                        PageRank / lazy rules: FIFO_DENSE.  Default.                      */
+    ARCTE_ENGINE_FIFO_DENSE = 0,     /* one queue entry per warp iteration, dense {s, r} array per walk     */
+    ARCTE_ENGINE_BATCHED_DENSE = 1,  /* up to 32 queue entries (64 stored entries) per warp iteration staged
+                                        in shared memory, dense {s, r} array per walk                       */
+    ARCTE_ENGINE_BATCHED_HASH = 2    /* the same batches, walk state in a growing open-addressing table of
+                                        32-byte entries per walk (one sector per touched node)              */
+};
+
 /* Counters and device timings of the last arcte_cuda_extract/assemble on this context. */
 typedef struct arcte_cuda_stats {
     int64_t n_seeds_total;   /* seeds selected on the graph (arcte.py:614-617)              */
@@ -85,6 +98,8 @@ typedef struct arcte_cuda_stats {
     double ms_assemble;      /* K5: pack, transpose, splice                                    */
     double alg_bytes_push;   /* SURVEY 8(d) algorithmic bytes of the push kernel              */
     double slot_utilisation; /* mean busy time of a walk state / span of the push launch      */
+    double ms_exchange;      /* multi-GPU: the all-to-all of community members (NCCL)          */
+    int64_t engine;          /* ARCTE_ENGINE_* that walked the last extraction (-2: frontier)  */
 } arcte_cuda_stats;
 
 /* -- lifetime ------------------------------------------------------------- */
@@ -106,6 +121,12 @@ int arcte_cuda_configure(arcte_cuda_ctx *ctx, int warps_per_sm, int64_t queue_ca
    light_threads threads (threads: 32, 64, 128, 256, 512 or 1024). */
 int arcte_cuda_set_schedule(arcte_cuda_ctx *ctx, int schedule, int heavy_permille, int heavy_threads,
                             int heavy_ctas_per_sm, int light_threads, int light_ctas_per_sm);
+
+/* Selects the engine of the FIFO schedule (ARCTE_ENGINE_*); table_capacity > 0 bounds the entries of one
+   walk's hash table half (rounded up to a power of two; a walk that outgrows it is re-run by
+   ARCTE_ENGINE_FIFO_DENSE), 0 = as many as 2n or the memory budget allows.  The environment variable
+   ARCTE_CUDA_ENGINE=fifo|dense|hash overrides AUTO. */
+int arcte_cuda_set_engine(arcte_cuda_ctx *ctx, int engine, int64_t table_capacity);
 
 /* -- a11 + a1: graph upload and transition build --------------------------- */
 /* Replaces the pickled (indices, indptr, data) hand-off of arcte.py:657-665 and

@@ -15,10 +15,11 @@ LIB_PATH = os.environ.get("ARCTE_CUDA_LIB") or os.path.join(_HERE, "libarcte_cud
 
 RULE_ABSORBING, RULE_PAGERANK, RULE_LAZY = 0, 1, 2
 SCHEDULE_FIFO, SCHEDULE_FRONTIER = 0, 1
+ENGINE_AUTO, ENGINE_FIFO_DENSE, ENGINE_BATCHED_DENSE, ENGINE_BATCHED_HASH = -1, 0, 1, 2
 
 # every symbol include/arcte_cuda.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    "arcte_cuda_device_count", "arcte_cuda_create", "arcte_cuda_destroy", "arcte_cuda_last_error", "arcte_cuda_configure", "arcte_cuda_set_schedule",
+    "arcte_cuda_device_count", "arcte_cuda_create", "arcte_cuda_destroy", "arcte_cuda_last_error", "arcte_cuda_configure", "arcte_cuda_set_schedule", "arcte_cuda_set_engine",
     "arcte_cuda_set_graph", "arcte_cuda_set_transition", "arcte_cuda_set_seeds", "arcte_cuda_build_transition", "arcte_cuda_get_transition",
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
     "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
@@ -36,7 +37,8 @@ class Stats(C.Structure):
         "n_seeds_total", "n_seeds_shard", "pushes", "edge_touches", "enqueues", "max_queue",
         "support", "touched", "seed_degree", "members", "emitted", "retries", "n_slots",
         "launches", "rounds")] + [(k, C.c_double) for k in (
-            "ms_transition", "ms_seeds", "ms_push", "ms_assemble", "alg_bytes_push", "slot_utilisation")]
+            "ms_transition", "ms_seeds", "ms_push", "ms_assemble", "alg_bytes_push", "slot_utilisation",
+            "ms_exchange")] + [("engine", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,6 +74,7 @@ def load():
         L.arcte_cuda_destroy.restype = None
         L.arcte_cuda_configure.argtypes = [vp, i32, i64, i32, i64]
         L.arcte_cuda_set_schedule.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+        L.arcte_cuda_set_engine.argtypes = [vp, i32, i64]
         L.arcte_cuda_set_graph.argtypes = [vp, i64, i64, vp, vp, vp]
         L.arcte_cuda_set_transition.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
         L.arcte_cuda_set_seeds.argtypes = [vp, i64, vp]

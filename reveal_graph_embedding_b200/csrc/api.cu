@@ -128,6 +128,8 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
                        &c->fo_indptr[0], &c->fo_indptr[1], &c->fo_indices[0], &c->fo_indices[1], &c->fo_data[0], &c->fo_data[1]};
     for (DevBuf *b : fbufs) dev_free(*b);
     for (DevBuf &b : c->peer_stage) dev_free(b);
+    DevBuf *pbufs[] = {&c->bpool.tbl, &c->bpool.stage, &c->bpool.clean, &c->bpool.queue, &c->row_w};
+    for (DevBuf *b : pbufs) dev_free(*b);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->tm0);
@@ -176,6 +178,19 @@ int arcte_cuda_set_schedule(arcte_cuda_ctx *c, int schedule, int heavy_permille,
     return ARCTE_OK;
 }
 
+int arcte_cuda_set_engine(arcte_cuda_ctx *c, int engine, int64_t table_capacity)
+{
+    CHECK_CTX(c);
+    if (engine < ARCTE_ENGINE_AUTO || engine > ARCTE_ENGINE_BATCHED_HASH || table_capacity < 0 ||
+        table_capacity > (int64_t(1) << 26)) {
+        set_error("set_engine: argument out of range");
+        return ARCTE_E_ARG;
+    }
+    c->engine = engine;
+    c->tbl_cap_cfg = table_capacity;
+    return ARCTE_OK;
+}
+
 int arcte_cuda_set_graph(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_t *host_indptr,
                          const int32_t *host_indices, const double *host_data);
 
@@ -193,6 +208,7 @@ static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int
         return ARCTE_E_ARG;
     }
     c->have_graph = c->have_transition = c->have_segments = c->have_features = false;
+    c->row_w_valid = false;
     if (n != c->n) {
         // slot geometry depends on n: drop the pool (re-created lazily)
         dev_free(c->slots.sr);

@@ -76,9 +76,19 @@ struct SlotPool {
 enum PushCounter {
     PC_PUSHES = 0, PC_EDGES, PC_ENQUEUES, PC_MAXQ, PC_SUPPORT, PC_TOUCHED, PC_SEEDDEG, PC_MEMBERS,
     PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR,
-    PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS,
+    PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS, PC_TOVERFLOW,
     PC_PROF0, PC_PROF1, PC_PROF2, PC_PROF3, PC_PROF4, PC_PROF5, PC_PROF6, PC_PROF7, PC_PROF8, PC_PROF9,  // kernel experiments
     PC_COUNT
+};
+
+// Slot pool of the batched hash engine (push_batched.cu): per slot two table halves of `cap` 32-byte
+// entries, a member staging list of `cap` ints and a FIFO ring.
+struct BatchedPool {
+    DevBuf tbl;     // TableEntry [n_slots][2][cap]
+    DevBuf stage;   // int32 [n_slots][cap]
+    DevBuf clean;   // int32 [n_slots][2]  entries of each half known all-EMPTY
+    DevBuf queue;   // int32 [n_slots][queue_cap]
+    int64_t n_slots = 0, cap = 0, plan_cap = 0, queue_cap = 0, queue_slots = 0;
 };
 
 }  // namespace arcte
@@ -98,6 +108,8 @@ struct arcte_cuda_ctx {
     int mem_percent = 0;       // 0 = default
     int64_t member_cap_cfg = 0; // 0 = default
     int schedule = 0;          // ARCTE_SCHEDULE_FIFO (exact) or ARCTE_SCHEDULE_FRONTIER
+    int engine = -1;           // ARCTE_ENGINE_* of the FIFO schedule
+    int64_t tbl_cap_cfg = 0;   // 0 = default
     int fr_heavy_permille = -1, fr_heavy_threads = 0, fr_heavy_ctas = 0, fr_light_threads = 0, fr_light_ctas = 0;
 
     // graph (adjacency + transition), all resident
@@ -128,6 +140,9 @@ struct arcte_cuda_ctx {
     bool have_segments = false;
 
     arcte::SlotPool slots;
+    arcte::BatchedPool bpool;
+    arcte::DevBuf row_w;       // double [n]  the repeated transition weight of each row (uniform_rows)
+    bool row_w_valid = false, uniform_rows = false;
     arcte::DevBuf counters;  // int64 [PC_COUNT]
 
     // assembly output

@@ -21,112 +21,13 @@
 // within the push error bound.  Thousands of slots are in flight per GPU; seeds are
 // pulled from a degree-descending work list through one atomic counter.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "push.cuh"
 
 namespace arcte {
 
-
-__device__ __forceinline__ double warp_min(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_sum_i(int v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
-
-// State pairs are gathered at random over gigabytes: keep them out of L1 (L2-only loads and
-// stores) so L1 stays with what is re-read -- the FIFO ring, the touched list, node records,
-// CSR rows and the few spilled registers.
-//
-// L2 eviction hints (experiment switches, see profiles/README.md):
-//   ARCTE_HINT_STATE  state pairs are loaded/stored with an L2 evict_first policy (they stream
-//                     through L2: the next use of a sector is milliseconds away);
-//   ARCTE_HINT_GRAPH  node records, column indices and transition weights are loaded with an
-//                     L2 evict_last policy (90 MB on the YouTube shape, re-read by every walk).
-// The policies are created once per thread (createpolicy is a register-only instruction).
-#ifndef ARCTE_HINT_STATE
-#define ARCTE_HINT_STATE 0
-#endif
-#ifndef ARCTE_HINT_GRAPH
-#define ARCTE_HINT_GRAPH 0
-#endif
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-#if ARCTE_HINT_STATE
-__device__ __forceinline__ double2 ld_state(const double2 *p)
-{
-    double2 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
-                 : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(l2_policy_evict_first()) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_state(double2 *p, double2 v)
-{
-    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;"
-                 :: "l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_evict_first()) : "memory");
-}
-#elif !defined(ARCTE_STATE_L1)
-__device__ __forceinline__ double2 ld_state(const double2 *p) { return __ldcg(p); }
-__device__ __forceinline__ void st_state(double2 *p, double2 v) { __stcg(p, v); }
-#else
-__device__ __forceinline__ double2 ld_state(const double2 *p) { return *p; }
-__device__ __forceinline__ void st_state(double2 *p, double2 v) { *p = v; }
-#endif
-#if ARCTE_HINT_GRAPH
-__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p)
-{
-    NodeInfo v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
-                 : "=l"(*reinterpret_cast<unsigned long long *>(&v.d_in)),
-                   "=l"(*reinterpret_cast<unsigned long long *>(&v.begin))
-                 : "l"(p), "l"(l2_policy_evict_last()));
-    return v;
-}
-__device__ __forceinline__ double ld_info_din(const NodeInfo *p)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(&p->d_in), "l"(l2_policy_evict_last()));
-    return v;
-}
-__device__ __forceinline__ int ld_index(const int32_t *p)
-{
-    int v;
-    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_last()));
-    return v;
-}
-__device__ __forceinline__ double ld_weight(const double *p)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(l2_policy_evict_last()));
-    return v;
-}
-#else
-__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p) { return *p; }
-__device__ __forceinline__ double ld_info_din(const NodeInfo *p) { return p->d_in; }
-__device__ __forceinline__ int ld_index(const int32_t *p) { return *p; }
-__device__ __forceinline__ double ld_weight(const double *p) { return *p; }
-#endif
-
-// Per-warp statistics live in shared memory (no registers held across the walk).
-enum WarpStat { WS_PUSHES = 0, WS_EDGES, WS_ENQ, WS_MAXQ, WS_SUPPORT, WS_TOUCHED, WS_SEEDDEG, WS_MEMBERS,
-                WS_EMITTED, WS_T_BEGIN, WS_COUNT };
 
 // Walk state of the warp for the current seed (all lanes hold the same values).
 struct Walk {
@@ -637,6 +538,21 @@ static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64
     return ARCTE_OK;
 }
 
+// Which engine of the FIFO schedule walks this call (include/arcte_cuda.h, ARCTE_ENGINE_*).
+static int resolve_engine(const arcte_cuda_ctx *c, int rule)
+{
+    if (rule != ARCTE_RULE_ABSORBING) return ARCTE_ENGINE_FIFO_DENSE;
+    int e = c->engine;
+    if (e == ARCTE_ENGINE_AUTO) {
+        const char *env = getenv("ARCTE_CUDA_ENGINE");
+        if (env && !strcmp(env, "fifo")) e = ARCTE_ENGINE_FIFO_DENSE;
+        else if (env && !strcmp(env, "dense")) e = ARCTE_ENGINE_BATCHED_DENSE;
+        else if (env && !strcmp(env, "hash")) e = ARCTE_ENGINE_BATCHED_HASH;
+    }
+    if (e == ARCTE_ENGINE_AUTO) e = c->n > (int64_t(1) << 18) ? ARCTE_ENGINE_BATCHED_HASH : ARCTE_ENGINE_BATCHED_DENSE;
+    return e;
+}
+
 int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int shard_rank,
                   int shard_count, const double *host_eps_override)
 {
@@ -694,13 +610,19 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         return ARCTE_E_ARG;
     }
     int64_t n_slots = 0, qcap = 0;
+    const int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
+    const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
     if (frontier) {
         ARCTE_TRY(frontier_plan_slots(c, S, &n_slots));
         ARCTE_TRY(frontier_ensure_slots(c, n_slots));
+    } else if (batched) {
+        ARCTE_TRY(batched_plan(c, engine, S, &n_slots, &qcap));
+        ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
     } else {
         ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap));
         ARCTE_TRY(ensure_slots(c, n_slots, qcap));
     }
+    stt.engine = frontier ? -2 : engine;
     if (c->member_cap == 0) {
         // default: a tenth of what is free now, never more than the n_seeds x n worst case
         size_t free_b = 0, total_b = 0;
@@ -745,6 +667,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.scale = frontier_scale(rho);
         P.inv_scale = 1.0 / P.scale;
     }
+    if (batched) batched_fill_params(c, engine, P);
 
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.as<int64_t>() + PC_T_START, 0xff, sizeof(int64_t), st));
@@ -752,6 +675,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     const cudaEvent_t p0 = c->pk0, p1 = c->pk1;  // owned by the context: nothing to release on the error paths
     ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
     if (frontier) ARCTE_TRY(frontier_launch(c, P, S, false));
+    else if (batched) ARCTE_TRY(batched_launch(c, engine, P));
     else ARCTE_TRY(launch_push(c, rule, P));
     ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
 
@@ -776,9 +700,20 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         const int64_t n_retry = hc[PC_OVERFLOW_SEEDS];
         stt.retries += n_retry;
         if (++rounds > 12) { set_error("extract: retry passes did not converge"); return ARCTE_E_OVERFLOW; }
+        if (batched && rounds == 1) {
+            // seeds the batched engine gave up on (ring, table region or member range too small) are re-run
+            // by the dense FIFO engine: same results, and its rings grow as far as memory allows
+            int64_t ls = 0, lq = 0;
+            ARCTE_TRY(plan_slots(c, n_retry, &ls, &lq));
+            ARCTE_TRY(ensure_slots(c, ls, lq));
+            P.sr = c->slots.sr.as<double2>();
+            P.touched = c->slots.touched.as<int32_t>();
+            P.queue = c->slots.queue.as<int32_t>();
+            P.queue_cap = c->slots.queue_cap;
+        }
         // members: grow to the exact demand seen so far (+ headroom for the seeds still to run)
-        if (hc[PC_MEMBER_CURSOR] > c->member_cap || hc[PC_QOVERFLOW] > 0) {
-            int64_t new_cap = hc[PC_MEMBER_CURSOR] + (hc[PC_QOVERFLOW] > 0 ? c->member_cap : 0);
+        if (hc[PC_MEMBER_CURSOR] > c->member_cap || hc[PC_QOVERFLOW] > 0 || hc[PC_TOVERFLOW] > 0) {
+            int64_t new_cap = hc[PC_MEMBER_CURSOR] + (hc[PC_QOVERFLOW] + hc[PC_TOVERFLOW] > 0 ? c->member_cap : 0);
             if (new_cap > c->member_cap) {
                 DevBuf nb;
                 ARCTE_TRY(dev_reserve(nb, sizeof(int32_t) * (size_t)new_cap));
@@ -822,6 +757,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
                                        cudaMemcpyHostToDevice, st));
         ARCTE_CUDA_TRY(cudaMemcpyAsync(c->counters.as<int64_t>() + PC_QOVERFLOW, &zero, sizeof(zero),
                                        cudaMemcpyHostToDevice, st));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->counters.as<int64_t>() + PC_TOVERFLOW, &zero, sizeof(zero),
+                                       cudaMemcpyHostToDevice, st));
         P.work_ids = c->scratch[0].as<int32_t>();
         P.n_work = n_retry;
         P.retry_pass = 1;
@@ -832,7 +769,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.member_cap = c->member_cap;
         ARCTE_CUDA_TRY(cudaEventRecord(p0, st));
         if (frontier) ARCTE_TRY(frontier_launch(c, P, n_retry, true));
-        else ARCTE_TRY(launch_push(c, rule, P));
+        else ARCTE_TRY(launch_push(c, rule, P));   // batched engines too: see above
         ARCTE_CUDA_TRY(cudaEventRecord(p1, st));
         ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
@@ -875,14 +812,7 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         set_error("push: the frontier schedule implements the absorbing rule only");
         return ARCTE_E_ARG;
     }
-    int64_t n_slots = 0, qcap = 0;
-    if (frontier) {
-        ARCTE_TRY(frontier_plan_slots(c, 1, &n_slots));
-        ARCTE_TRY(frontier_ensure_slots(c, n_slots));
-    } else {
-        ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
-        ARCTE_TRY(ensure_slots(c, n_slots, qcap));
-    }
+    int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
     ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * 4));
     ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * 4));
@@ -890,10 +820,29 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
     const int32_t seed32 = (int32_t)seed;
     ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[0].p, &seed32, sizeof(seed32), cudaMemcpyHostToDevice, st));
     ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[2].p, &eps_eff, sizeof(eps_eff), cudaMemcpyHostToDevice, st));
-    ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
+    double *s_dev = c->scratch[3].as<double>();
+    double *r_dev = s_dev + c->n;
 
-    int64_t cap = c->slots.queue_cap;
+    int64_t cap = 0;
+    bool pools_ready = false;
     for (int attempt = 0;; ++attempt) {
+        const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
+        if (!pools_ready) {
+            int64_t n_slots = 0, qcap = 0;
+            if (frontier) {
+                ARCTE_TRY(frontier_plan_slots(c, 1, &n_slots));
+                ARCTE_TRY(frontier_ensure_slots(c, n_slots));
+            } else if (batched) {
+                ARCTE_TRY(batched_plan(c, engine, 1, &n_slots, &qcap));
+                ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
+            } else {
+                ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
+                ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+            }
+            cap = c->slots.queue_cap;
+            pools_ready = true;
+        }
+        ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
         PushParams P{};
         P.n = c->n;
         P.info = c->node_info.as<NodeInfo>();
@@ -912,11 +861,18 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.debug_keep = 1;
         fill_rule_constants(P, rho);
         double inv_scale = 0.0;
+        const bool hash = batched && engine == ARCTE_ENGINE_BATCHED_HASH;
         if (frontier) {
             P.scale = frontier_scale(rho);
             P.inv_scale = inv_scale = 1.0 / P.scale;
             P.cursor = PC_WORK_CURSOR;
             ARCTE_TRY(frontier_launch(c, P, 1, false));
+        } else if (batched) {
+            batched_fill_params(c, engine, P);
+            P.dbg_s = s_dev;
+            P.dbg_r = r_dev;
+            if (hash) ARCTE_CUDA_TRY(cudaMemsetAsync(s_dev, 0, sizeof(double) * 2 * (size_t)c->n, st));
+            ARCTE_TRY(batched_launch(c, engine, P));
         } else {
             ARCTE_TRY(launch_push(c, rule, P));
         }
@@ -924,15 +880,15 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         ARCTE_CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
         const int64_t nt = hc[PC_TOUCHED];
-        double *s_dev = c->scratch[3].as<double>();
-        double *r_dev = s_dev + c->n;
         if (hc[PC_OVERFLOW_SEEDS] == 0) {
-            k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0, inv_scale);
-            ++c->stats.launches;
+            if (!hash) {
+                k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0, inv_scale);
+                ++c->stats.launches;
+            }
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_s, s_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_r, r_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
         }
-        if (nt > 0) {
+        if (nt > 0 && !hash) {   // the hash engine leaves its table empty itself
             k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1, inv_scale);
             ++c->stats.launches;
         }
@@ -940,6 +896,11 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         if (hc[PC_OVERFLOW_SEEDS] == 0) {
             if (n_push) *n_push = hc[PC_PUSHES];
             return ARCTE_OK;
+        }
+        if (batched) {   // ring or table region too small: the dense FIFO engine takes the seed (its ring grows below)
+            engine = ARCTE_ENGINE_FIFO_DENSE;
+            pools_ready = false;
+            continue;
         }
         // ring too small for this seed: one walk only, so give it one big ring
         const int64_t next = cap * 8;
@@ -955,7 +916,6 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
             c->slots.queue_slots = 1;  // the next plan_slots re-creates the per-slot rings
         }
         cap = next;
-        ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
     }
 }
 

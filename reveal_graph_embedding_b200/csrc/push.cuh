@@ -1,11 +1,23 @@
 // push.cuh -- parameters shared by the two walk schedules of the push engine:
 //   push.cu           exact FIFO replay of the reference's queue discipline (default)
+//   push_batched.cu   the same exact FIFO order, several queue entries per warp iteration, walk state
+//                     in a compact per-walk hash table (or dense), shared-memory staging (default)
 //   push_frontier.cu  synchronous frontier rounds on fixed-point state (opt-in, tolerance parity)
 #pragma once
 
 #include "common.cuh"
 
 namespace arcte {
+
+// Walk-state entry of the hash engine: ONE 32-byte sector per touched node, read and written with
+// single 256-bit accesses.  d_in rides along so that neither the enqueue test of a re-touch nor the
+// threshold sweep has to gather the node record again.
+struct __align__(32) TableEntry {
+    double s, r, d_in;
+    int32_t key;   // node id, kEmptyKey when free
+    int32_t aux;
+};
+constexpr int32_t kEmptyKey = -1;
 
 struct PushParams {
     int64_t n;
@@ -45,12 +57,130 @@ struct PushParams {
     double inv_scale;      // 2^-F
     int64_t work_lo;       // first work-list position of this launch (work_ids == nullptr)
     int cursor;            // PushCounter index of the work cursor this launch pulls from
+    // batched engine (push_batched.cu)
+    int64_t touched_stride;    // ints per slot in `touched` (dense: n; hash: the member staging list)
+    TableEntry *tbl;           // [n_slots][2][tbl_cap_max] open-addressing tables (two halves: grow = move)
+    int64_t tbl_cap_max;       // entries per half, power of two
+    int32_t *tbl_clean;        // [n_slots][2] entries of each half known to be all-EMPTY from index 0
+    double *dbg_s, *dbg_r;     // operator seam: dense s / r of the single walked seed (pre-zeroed)
+    int uniform_rows;          // 1: every row of w holds one repeated value, kept in row_w
+    const double *row_w;       // [n] that value (uniform_rows)
 };
+
+
+// Implemented in push_batched.cu.
+int batched_plan(arcte_cuda_ctx *c, int engine, int64_t n_work, int64_t *n_slots, int64_t *queue_cap);
+int batched_ensure(arcte_cuda_ctx *c, int engine, int64_t n_slots, int64_t queue_cap);
+void batched_fill_params(arcte_cuda_ctx *c, int engine, PushParams &P);
+int batched_launch(arcte_cuda_ctx *c, int engine, const PushParams &P);
 
 // Implemented in push_frontier.cu.
 int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots);
 int frontier_ensure_slots(arcte_cuda_ctx *c, int64_t n_slots);
 int frontier_launch(arcte_cuda_ctx *c, PushParams P, int64_t n_work, bool retry_pass);
 double frontier_scale(double rho);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// State pairs are gathered at random over gigabytes: keep them out of L1 (L2-only loads and
+// stores) so L1 stays with what is re-read -- the FIFO ring, the touched list, node records,
+// CSR rows and the few spilled registers.
+//
+// L2 eviction hints (experiment switches, see profiles/README.md):
+//   ARCTE_HINT_STATE  state pairs are loaded/stored with an L2 evict_first policy (they stream
+//                     through L2: the next use of a sector is milliseconds away);
+//   ARCTE_HINT_GRAPH  node records, column indices and transition weights are loaded with an
+//                     L2 evict_last policy (90 MB on the YouTube shape, re-read by every walk).
+// The policies are created once per thread (createpolicy is a register-only instruction).
+#ifndef ARCTE_HINT_STATE
+#define ARCTE_HINT_STATE 0
+#endif
+#ifndef ARCTE_HINT_GRAPH
+#define ARCTE_HINT_GRAPH 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#if ARCTE_HINT_STATE
+__device__ __forceinline__ double2 ld_state(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(l2_policy_evict_first()) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(double2 *p, double2 v)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;"
+                 :: "l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_evict_first()) : "memory");
+}
+#elif !defined(ARCTE_STATE_L1)
+__device__ __forceinline__ double2 ld_state(const double2 *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_state(double2 *p, double2 v) { __stcg(p, v); }
+#else
+__device__ __forceinline__ double2 ld_state(const double2 *p) { return *p; }
+__device__ __forceinline__ void st_state(double2 *p, double2 v) { *p = v; }
+#endif
+#if ARCTE_HINT_GRAPH
+__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p)
+{
+    NodeInfo v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                 : "=l"(*reinterpret_cast<unsigned long long *>(&v.d_in)),
+                   "=l"(*reinterpret_cast<unsigned long long *>(&v.begin))
+                 : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ double ld_info_din(const NodeInfo *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(&p->d_in), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ int ld_index(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+__device__ __forceinline__ double ld_weight(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(l2_policy_evict_last()));
+    return v;
+}
+#else
+__device__ __forceinline__ NodeInfo ld_info(const NodeInfo *p) { return *p; }
+__device__ __forceinline__ double ld_info_din(const NodeInfo *p) { return p->d_in; }
+__device__ __forceinline__ int ld_index(const int32_t *p) { return *p; }
+__device__ __forceinline__ double ld_weight(const double *p) { return *p; }
+#endif
+
+// Per-warp statistics live in shared memory (no registers held across the walk).
+enum WarpStat { WS_PUSHES = 0, WS_EDGES, WS_ENQ, WS_MAXQ, WS_SUPPORT, WS_TOUCHED, WS_SEEDDEG, WS_MEMBERS,
+                WS_EMITTED, WS_T_BEGIN, WS_COUNT };
+
+#endif  // __CUDACC__
 
 }  // namespace arcte

@@ -14,6 +14,8 @@
 // The second needs the column's entries in row order, i.e. a transposition; it is done
 // with the stable radix sort (key = column, value = weight) so no atomics on doubles and
 // no run-to-run variation.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "primitives.cuh"
 
@@ -220,6 +222,26 @@ static int bit_length(uint64_t v)
 
 static inline unsigned grid_for(int64_t items, int block) { return (unsigned)((items + block - 1) / block); }
 
+// Row-uniform transition weights (every unweighted graph: w[u][:] = 1/d_out[u]): the batched engine then
+// reads one weight per pushed row instead of one per stored entry.  One warp per row.
+__global__ void k_row_uniform(int64_t n, const NodeInfo *__restrict__ info, const double *__restrict__ w,
+                              double *__restrict__ row_w, unsigned long long *__restrict__ any_nonuniform)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const NodeInfo iu = info[row];
+    const double w0 = iu.len ? w[iu.begin] : 0.0;
+    bool same = true;
+    for (unsigned j = lane; j < iu.len; j += 32)
+        same = same && (__double_as_longlong(w[iu.begin + j]) == __double_as_longlong(w0));
+    same = __all_sync(kFull, same);
+    if (lane == 0) {
+        row_w[row] = w0;
+        if (!same) atomicOr(any_nonuniform, 1ull);
+    }
+}
+
 // ---- K2a: seeds, count-descending (ties: ascending node id); needs colcnt ----
 int select_seeds(arcte_cuda_ctx *c)
 {
@@ -247,18 +269,24 @@ int select_seeds(arcte_cuda_ctx *c)
     ARCTE_TRY(dev_reserve(c->scratch[1], sizeof(uint32_t) * m));
     ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(uint32_t) * m));
     ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(uint32_t) * m));
-    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * 2));
+    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * 4));
     ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
+    ARCTE_TRY(dev_reserve(c->row_w, sizeof(double) * (size_t)n));
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
     int64_t *tmp2 = c->scratch[7].as<int64_t>();
-    ARCTE_CUDA_TRY(cudaMemsetAsync(tmp2, 0, 2 * sizeof(int64_t), st));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(tmp2, 0, 3 * sizeof(int64_t), st));
     k_count_stats<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), tmp2);
     ++*launches;
-    int64_t host2[2];
+    k_row_uniform<<<grid_for(n * 32, 256), 256, 0, st>>>(n, c->node_info.as<NodeInfo>(), c->w.as<double>(),
+                                                        c->row_w.as<double>(), (unsigned long long *)(tmp2 + 2));
+    ++*launches;
+    int64_t host2[3];
     ARCTE_CUDA_TRY(cudaMemcpyAsync(host2, tmp2, sizeof(host2), cudaMemcpyDeviceToHost, st));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     const int32_t maxcnt = (int32_t)host2[0];
     c->n_seeds = host2[1];
+    c->uniform_rows = host2[2] == 0 && !getenv("ARCTE_CUDA_NO_UNIFORM");
+    c->row_w_valid = true;
     k_seed_keys<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), maxcnt,
                                                   c->scratch[0].as<uint32_t>(),
                                                   (uint32_t *)c->scratch[2].p);

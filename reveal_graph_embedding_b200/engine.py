@@ -102,6 +102,16 @@ class Engine:
                                               int(heavy_ctas_per_sm), int(light_threads), int(light_ctas_per_sm)))
         self.schedule = _SCHEDULES[schedule]
 
+    def set_engine(self, engine="auto", table_capacity=0):
+        """Engine of the exact FIFO schedule (include/arcte_cuda.h: ARCTE_ENGINE_*): "auto", "fifo" (one
+        queue entry per warp iteration, dense state), "dense" (batched, dense state) or "hash" (batched,
+        compact per-walk hash tables).  All of them give bit-identical results."""
+        names = {"auto": _lib.ENGINE_AUTO, "fifo": _lib.ENGINE_FIFO_DENSE, "dense": _lib.ENGINE_BATCHED_DENSE,
+                 "hash": _lib.ENGINE_BATCHED_HASH}
+        if engine not in names:
+            raise ValueError("unknown engine %r" % (engine,))
+        check(self._L.arcte_cuda_set_engine(self._h, names[engine], int(table_capacity)))
+
     # -- a11 + a1 -------------------------------------------------------------------------
     def set_graph(self, adjacency_matrix, canonical=False):
         """Upload the adjacency CSR and build the transition matrix (K1) and seed list (K2a)."""
