@@ -210,9 +210,32 @@ int arcte_cuda_assemble_rows(arcte_cuda_ctx *ctx, int n_parts, const int64_t *pa
                              int64_t *nnz_out);
 int arcte_cuda_get_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *host_indices,
                             double *host_data);
+/* The same copy for callers that know the values: with values_are_ones != 0 host_data is not copied but
+   written as 1.0 by the host threads that stream the indices in (every stored value of the feature matrix
+   is 1.0 except the identity entry of a self-loop row, which the caller patches to 2.0: arcte.py:379-381,
+   :676-679).  Destinations are ordinary pageable memory (numpy arrays); the copy runs through a small
+   fixed ring of pinned slots on n_threads host threads (<= 0: all, at most 16). */
+int arcte_cuda_fetch_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t *host_indices, double *host_data,
+                              int values_are_ones, int n_threads);
 /* Device-resident views of the assembled block (for a collective library). */
 int arcte_cuda_features_device(arcte_cuda_ctx *ctx, const int64_t **dev_indptr, const int32_t **dev_indices,
                                const double **dev_data, int64_t *n_rows, int64_t *nnz);
+
+/* -- e: the multi-GPU exchange, inside the library (arcte.py:650-673) ------------------------
+   Rank r of `world` walks shard r (arcte_cuda_extract with shard_rank = r, shard_count = world) and owns the
+   rows [n r / world, n (r+1) / world) of the result.  arcte_cuda_exchange_assemble splits every community by
+   destination row block on the device, exchanges the pieces with one grouped NCCL send/recv (an all-to-all:
+   each member crosses NVLink at most once, values are never sent) and assembles this rank's row block
+   (arcte_cuda_features_device / _fetch_features then see that block).  NCCL is loaded at run time
+   (libnccl.so.2).  One process per GPU: rank 0 calls arcte_cuda_comm_unique_id, the caller distributes the
+   128 bytes (e.g. torch.distributed.broadcast), every rank calls arcte_cuda_comm_init.  One process driving
+   several GPUs: arcte_cuda_comm_init_all over its contexts (rank = position), then one host thread per
+   context calls arcte_cuda_exchange_assemble concurrently. */
+int arcte_cuda_comm_unique_id(void *id_out_128_bytes);
+int arcte_cuda_comm_init(arcte_cuda_ctx *ctx, int world, int rank, const void *id_128_bytes);
+int arcte_cuda_comm_init_all(arcte_cuda_ctx *const *ctxs, int n);
+int arcte_cuda_comm_info(arcte_cuda_ctx *ctx, int *world, int *rank, int *nccl_version);
+int arcte_cuda_exchange_assemble(arcte_cuda_ctx *ctx, int64_t *nnz_out);
 
 /* -- after the path: column normalisation and community weighting ---------- */
 /* These take and return HOST CSR arrays (canonical: sorted column indices) like the reference

@@ -1,4 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/arcte_cuda.h.
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -13,6 +15,10 @@ int dev_reserve(DevBuf &b, size_t bytes)
 {
     if (bytes == 0) bytes = 16;
     if (b.bytes >= bytes) return ARCTE_OK;
+    if (b.borrowed) {
+        set_error("internal: a view into the graph arena cannot grow");
+        return ARCTE_E_ARG;
+    }
     if (b.p) {
         cudaFree(b.p);
         b.p = nullptr;
@@ -31,9 +37,10 @@ int dev_reserve(DevBuf &b, size_t bytes)
 
 void dev_free(DevBuf &b)
 {
-    if (b.p) cudaFree(b.p);
+    if (b.p && !b.borrowed) cudaFree(b.p);
     b.p = nullptr;
     b.bytes = 0;
+    b.borrowed = false;
 }
 
 // implemented in the other translation units
@@ -109,6 +116,24 @@ int arcte_cuda_create(arcte_cuda_ctx **out, int device_id)
     ARCTE_CUDA_TRY(cudaEventCreate(&c->tm1));
     ARCTE_CUDA_TRY(cudaEventCreate(&c->pk0));
     ARCTE_CUDA_TRY(cudaEventCreate(&c->pk1));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->xev0));
+    ARCTE_CUDA_TRY(cudaEventCreate(&c->xev1));
+    {   // Experiment switch, off by default: ARCTE_CUDA_L2_PERSIST_MB=<n> sets n MB of L2 aside for persisting
+        // accesses to the graph arena (upload_structure).  Measured on the bench shape it is a loss: the walks'
+        // own state needs the capacity more (profiles/r2_l2_persist.md).
+        const char *env = getenv("ARCTE_CUDA_L2_PERSIST_MB");
+        size_t want = env ? (size_t)atol(env) << 20 : 0;
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            c->l2_persist_bytes = want;
+            c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else {
+            (void)cudaGetLastError();
+        }
+        if (getenv("ARCTE_CUDA_DEBUG"))
+            fprintf(stderr, "[arcte] L2 %d MB, persisting max %d MB (set %zu MB), window max %d MB\n", prop.l2CacheSize >> 20,
+                    prop.persistingL2CacheMaxSize >> 20, c->l2_persist_bytes >> 20, prop.accessPolicyMaxWindowSize >> 20);
+    }
     *out = c;
     return ARCTE_OK;
 }
@@ -118,7 +143,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->edge_wd, &c->seeds,
+    DevBuf *bufs[] = {&c->graph_arena, &c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->edge_wd, &c->edge_din, &c->seeds,
                       &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
                       &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->slots.frontier, &c->slots.fval, &c->counters, &c->out_indptr,
                       &c->out_indices, &c->out_data};
@@ -136,7 +161,12 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     cudaEventDestroy(c->tm1);
     cudaEventDestroy(c->pk0);
     cudaEventDestroy(c->pk1);
+    cudaEventDestroy(c->xev0);
+    cudaEventDestroy(c->xev1);
+    comm_free(c);
+    for (DevBuf &b : c->xbuf) dev_free(b);
     dev_free(c->l2_flush);
+    free_ring(c);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -222,12 +252,38 @@ static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int
     c->nnz = nnz;
     c->stats = arcte_cuda_stats();
     ARCTE_TRY(dev_reserve(c->indptr, sizeof(int64_t) * (size_t)(n + 1)));
-    ARCTE_TRY(dev_reserve(c->indices, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(c->indptr.p, host_indptr, sizeof(int64_t) * (size_t)(n + 1),
-                                   cudaMemcpyHostToDevice, c->stream));
-    if (nnz > 0)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->indices.p, host_indices, sizeof(int32_t) * (size_t)nnz,
-                                       cudaMemcpyHostToDevice, c->stream));
+    {   // graph arena: node records, row weights, column indices, transition weights, in this order
+        auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+        const size_t b_info = up(sizeof(NodeInfo) * (size_t)n), b_rw = up(sizeof(double) * (size_t)n);
+        const size_t b_idx = up(sizeof(int32_t) * nz), b_w = up(sizeof(double) * nz);
+        DevBuf *views[] = {&c->node_info, &c->row_w, &c->indices, &c->w};
+        for (DevBuf *v : views) dev_free(*v);
+        ARCTE_TRY(dev_reserve(c->graph_arena, b_info + b_rw + b_idx + b_w));
+        char *base = c->graph_arena.as<char>();
+        const size_t sizes[] = {b_info, b_rw, b_idx, b_w};
+        for (int i = 0; i < 4; ++i) {
+            views[i]->p = base;
+            views[i]->bytes = sizes[i];
+            views[i]->borrowed = true;
+            base += sizes[i];
+        }
+        // L2 persistence: the walks re-read node records (random gathers), row weights and column indices
+        // millions of times while their own state streams through L2 once
+        if (c->l2_persist_bytes > 0) {
+            size_t win = b_info + b_rw + b_idx;
+            if (win > c->l2_window_max) win = c->l2_window_max;
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = c->graph_arena.p;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = win <= c->l2_persist_bytes ? 1.0f : (float)((double)c->l2_persist_bytes / (double)win);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            ARCTE_CUDA_TRY(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
+    }
+    ARCTE_TRY(copy_from_host(c, c->indptr.p, host_indptr, sizeof(int64_t) * (size_t)(n + 1)));
+    if (nnz > 0) ARCTE_TRY(copy_from_host(c, c->indices.p, host_indices, sizeof(int32_t) * (size_t)nnz));
     return ARCTE_OK;
 }
 
@@ -279,9 +335,7 @@ int arcte_cuda_set_graph(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int64_
     if (nnz > 0 && !host_data) { set_error("set_graph: null data"); return ARCTE_E_ARG; }
     ARCTE_TRY(upload_structure(c, n, nnz, host_indptr, host_indices));
     ARCTE_TRY(dev_reserve(c->adj, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
-    if (nnz > 0)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->adj.p, host_data, sizeof(double) * (size_t)nnz,
-                                       cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) ARCTE_TRY(copy_from_host(c, c->adj.p, host_data, sizeof(double) * (size_t)nnz));
     c->have_graph = true;
     return build_transition(c);
 }
@@ -495,14 +549,15 @@ int arcte_cuda_get_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *ho
 {
     CHECK_CTX(c);
     if (!c->have_features) { set_error("get_features: call assemble first"); return ARCTE_E_ARG; }
-    if (host_indptr)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->out_indptr.p, sizeof(int64_t) * (size_t)(c->out_rows + 1), cudaMemcpyDeviceToHost, c->stream));
-    if (host_indices && c->out_nnz > 0)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indices, c->out_indices.p, sizeof(int32_t) * (size_t)c->out_nnz, cudaMemcpyDeviceToHost, c->stream));
-    if (host_data && c->out_nnz > 0)
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_data, c->out_data.p, sizeof(double) * (size_t)c->out_nnz, cudaMemcpyDeviceToHost, c->stream));
-    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return ARCTE_OK;
+    return fetch_features(c, host_indptr, host_indices, host_data, 0, 0);
+}
+
+int arcte_cuda_fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data,
+                              int values_are_ones, int n_threads)
+{
+    CHECK_CTX(c);
+    if (!c->have_features) { set_error("fetch_features: call assemble first"); return ARCTE_E_ARG; }
+    return fetch_features(c, host_indptr, host_indices, host_data, values_are_ones, n_threads);
 }
 
 int arcte_cuda_host_alloc(void **out, int64_t bytes)

@@ -44,6 +44,7 @@ void set_error(const std::string &msg);
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    bool borrowed = false;  // a view into another allocation (the graph arena): never freed or regrown on its own
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 int dev_reserve(DevBuf &b, size_t bytes);  // grow-only, contents not preserved
@@ -78,18 +79,36 @@ enum PushCounter {
     PC_EMITTED, PC_OVERFLOW_SEEDS, PC_QOVERFLOW, PC_MEMBER_CURSOR, PC_WORK_CURSOR,
     PC_T_START, PC_T_END, PC_T_BUSY, PC_WORK_CURSOR2, PC_ROUNDS, PC_TOVERFLOW,
     PC_PROF0, PC_PROF1, PC_PROF2, PC_PROF3, PC_PROF4, PC_PROF5, PC_PROF6, PC_PROF7, PC_PROF8, PC_PROF9,  // kernel experiments
+    PC_PROF10, PC_PROF11, PC_PROF12, PC_PROF13, PC_PROF14, PC_PROF15, PC_PROF16, PC_PROF17, PC_PROF18, PC_PROF19,
     PC_COUNT
 };
 
 // Slot pool of the batched hash engine (push_batched.cu): per slot two table halves of `cap` 32-byte
 // entries, a member staging list of `cap` ints and a FIFO ring.
 struct BatchedPool {
-    DevBuf tbl;     // TableEntry [n_slots][2][cap]
-    DevBuf stage;   // int32 [n_slots][cap]
-    DevBuf clean;   // int32 [n_slots][2]  entries of each half known all-EMPTY
+    DevBuf tbl;     // hash: TableEntry [n_slots][2][cap]; direct: TableEntry [n_slots][cap], cap = n
+    DevBuf stage;   // int32 [n_slots][cap]  hash: member staging; direct: touched list, then members
+    DevBuf clean;   // int32 [n_slots][2]  hash: entries of each half known all-EMPTY; direct: [0] = last epoch used
     DevBuf queue;   // int32 [n_slots][queue_cap]
-    int64_t n_slots = 0, cap = 0, plan_cap = 0, queue_cap = 0, queue_slots = 0;
+    int64_t n_slots = 0, cap = 0, plan_cap = 0, cap_cfg = 0, queue_cap = 0, queue_slots = 0;
+    int mode = -1;  // engine the pool is laid out for
 };
+
+// Pinned staging ring of the streamed host copies (hostcopy.cu): two 4 MB slots, a stream and two events per
+// worker thread.
+constexpr int kMaxCopyThreads = 16;
+struct HostRing {
+    void *pinned = nullptr;
+    int n_threads = 0;
+    cudaStream_t streams[kMaxCopyThreads] = {};
+    cudaEvent_t events[2 * kMaxCopyThreads] = {};
+};
+int copy_to_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);
+int copy_from_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);
+int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data, int values_are_ones,
+                   int n_threads);
+void free_ring(arcte_cuda_ctx *c);
+void comm_free(arcte_cuda_ctx *c);
 
 }  // namespace arcte
 
@@ -100,7 +119,15 @@ struct arcte_cuda_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // caller-visible step timer
     cudaEvent_t pk0 = nullptr, pk1 = nullptr;  // around the push-kernel launches of one extraction
+    cudaEvent_t xev0 = nullptr, xev1 = nullptr;  // around the multi-GPU exchange
+
+    // multi-GPU exchange (exchange.cu): NCCL communicator (ncclComm_t), the shard the last extract walked
+    void *comm = nullptr;
+    int comm_world = 0, comm_rank = 0;
+    int shard_rank = 0, shard_count = 1;
+    arcte::DevBuf xbuf[5];
     arcte::DevBuf l2_flush;
+    arcte::HostRing ring;
 
     // tuning
     int warps_per_sm = 0;      // 0 = default
@@ -123,7 +150,12 @@ struct arcte_cuda_ctx {
     arcte::DevBuf colcnt;   // int32 [n]  binarised column counts
     arcte::DevBuf node_info; // NodeInfo [n]
     arcte::DevBuf edge_wd;   // double2 [nnz]  {transition weight, in-degree of the target} per stored entry
+    arcte::DevBuf edge_din;  // double [nnz]  in-degree of the target of every stored entry (batched engine)
     bool have_graph = false, have_transition = false;
+    // node_info | row_w | indices | w live back to back in one allocation so that ONE L2 access-policy
+    // window (persisting) can cover the arrays every walk re-reads
+    arcte::DevBuf graph_arena;
+    size_t l2_persist_bytes = 0, l2_window_max = 0;
 
     // seeds
     arcte::DevBuf seeds;    // int32 [n]  count-descending, first n_seeds valid

@@ -1,0 +1,235 @@
+// hostcopy.cu -- large copies between the device and ORDINARY (pageable) host memory at PCIe rate.
+//
+// The caller of arcte() hands over scipy arrays and gets scipy arrays back (arcte.py:591-688): plain
+// numpy memory.  A cudaMemcpy into pageable memory is staged by the driver through one small pinned
+// buffer at a few GB/s, and page-locking gigabytes per call (cudaHostRegister / cudaHostAlloc) costs more
+// than the copy it speeds up.  Instead the context owns a small fixed ring of pinned slots (2 per worker
+// thread, 4 MB each): every worker thread streams its share of the chunks device -> pinned slot with
+// cudaMemcpyAsync on its own stream and copies the previous slot into the caller's array while the next
+// chunk is in flight.  The first touch of the destination pages (a fresh numpy array is untouched
+// memory) is thereby spread over all the threads as well, and the range is advised to use huge pages.
+#include <sys/mman.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace arcte {
+
+constexpr size_t kSlotBytes = size_t(4) << 20;
+constexpr size_t kStreamedMin = size_t(8) << 20;  // below this one plain copy is as fast
+
+static int host_threads(int want)
+{
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int t = want > 0 ? want : hw;
+    if (t > hw) t = hw;
+    if (t > kMaxCopyThreads) t = kMaxCopyThreads;
+    return t;
+}
+
+static void advise_huge(void *p, size_t bytes)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    uintptr_t lo = ((uintptr_t)p + page - 1) & ~(uintptr_t)(page - 1);
+    uintptr_t hi = ((uintptr_t)p + bytes) & ~(uintptr_t)(page - 1);
+    if (hi > lo) (void)madvise((void *)lo, hi - lo, MADV_HUGEPAGE);  // best effort
+}
+
+static int ensure_ring(arcte_cuda_ctx *c, int threads)
+{
+    HostRing &r = c->ring;
+    if (r.pinned && r.n_threads >= threads) return ARCTE_OK;
+    if (r.pinned) {
+        cudaFreeHost(r.pinned);
+        r.pinned = nullptr;
+    }
+    ARCTE_CUDA_TRY(cudaHostAlloc(&r.pinned, (size_t)threads * 2 * kSlotBytes, cudaHostAllocPortable));
+    for (int t = r.n_threads; t < threads; ++t) {
+        ARCTE_CUDA_TRY(cudaStreamCreateWithFlags(&r.streams[t], cudaStreamNonBlocking));
+        ARCTE_CUDA_TRY(cudaEventCreateWithFlags(&r.events[2 * t], cudaEventDisableTiming));
+        ARCTE_CUDA_TRY(cudaEventCreateWithFlags(&r.events[2 * t + 1], cudaEventDisableTiming));
+    }
+    r.n_threads = threads;
+    return ARCTE_OK;
+}
+
+void free_ring(arcte_cuda_ctx *c)
+{
+    HostRing &r = c->ring;
+    for (int t = 0; t < r.n_threads; ++t) {
+        cudaStreamDestroy(r.streams[t]);
+        cudaEventDestroy(r.events[2 * t]);
+        cudaEventDestroy(r.events[2 * t + 1]);
+    }
+    if (r.pinned) cudaFreeHost(r.pinned);
+    r = HostRing();
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// One job = one contiguous range.  Several jobs run in the same pool of threads (chunks of all jobs are
+// dealt round-robin), host-side fills included, so that a copy and a fill overlap.
+struct CopyJob {
+    char *host;
+    char *dev;
+    size_t bytes;
+    bool to_host;
+};
+
+static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double *fill, size_t fill_count, double fill_value,
+                    int n_threads)
+{
+    struct Chunk { int job; size_t off, len; };   // job == -1: fill
+    std::vector<Chunk> copies, fills, chunks;
+    for (size_t j = 0; j < jobs.size(); ++j)
+        for (size_t off = 0; off < jobs[j].bytes; off += kSlotBytes)
+            copies.push_back({(int)j, off, std::min(kSlotBytes, jobs[j].bytes - off)});
+    const size_t fill_bytes = fill_count * sizeof(double);
+    for (size_t off = 0; off < fill_bytes; off += kSlotBytes) fills.push_back({-1, off, std::min(kSlotBytes, fill_bytes - off)});
+    // copy and fill chunks interleaved in proportion, so that the fills run while the PCIe copies are in flight
+    for (size_t a = 0, b = 0; a < copies.size() || b < fills.size();) {
+        if (b >= fills.size() || (a < copies.size() && a * fills.size() <= b * copies.size())) chunks.push_back(copies[a++]);
+        else chunks.push_back(fills[b++]);
+    }
+    if (chunks.empty()) return ARCTE_OK;
+    int T = host_threads(n_threads);
+    if ((size_t)T > chunks.size()) T = (int)chunks.size();
+    ARCTE_TRY(ensure_ring(c, T));
+    for (const CopyJob &j : jobs)
+        if (j.to_host) advise_huge(j.host, j.bytes);
+    if (fill) advise_huge(fill, fill_bytes);
+    // interleave copy and fill chunks so that every thread sees both kinds
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    HostRing &r = c->ring;
+    auto worker = [&](int t) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { failed = 1; return; }
+        char *slot[2] = {(char *)r.pinned + (size_t)(2 * t) * kSlotBytes, (char *)r.pinned + (size_t)(2 * t + 1) * kSlotBytes};
+        cudaStream_t st = r.streams[t];
+        int k = 0;
+        Chunk pending{};   // device -> host chunk whose slot still has to be copied out
+        int pending_slot = -1;
+        auto drain = [&]() {
+            if (pending_slot < 0) return;
+            if (cudaEventSynchronize(r.events[2 * t + pending_slot]) != cudaSuccess) failed = 1;
+            memcpy(jobs[pending.job].host + pending.off, slot[pending_slot], pending.len);
+            pending_slot = -1;
+        };
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= chunks.size() || failed) break;
+            const Chunk ch = chunks[i];
+            if (ch.job < 0) {
+                double *p = (double *)((char *)fill + ch.off);
+                std::fill(p, p + ch.len / sizeof(double), fill_value);
+                continue;
+            }
+            const CopyJob &jb = jobs[ch.job];
+            const int s = k & 1;
+            ++k;
+            if (jb.to_host) {
+                if (pending_slot == s) drain();
+                if (cudaMemcpyAsync(slot[s], jb.dev + ch.off, ch.len, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaEventRecord(r.events[2 * t + s], st) != cudaSuccess) {
+                    failed = 1;
+                    break;
+                }
+                const Chunk prev = pending;
+                const int prev_slot = pending_slot;
+                pending = ch;
+                pending_slot = s;
+                if (prev_slot >= 0 && prev_slot != s) {   // copy the previous chunk out while this one is in flight
+                    if (cudaEventSynchronize(r.events[2 * t + prev_slot]) != cudaSuccess) failed = 1;
+                    memcpy(jobs[prev.job].host + prev.off, slot[prev_slot], prev.len);
+                }
+            } else {
+                drain();
+                // the slot must not be overwritten while an earlier upload still reads it
+                if (cudaEventSynchronize(r.events[2 * t + s]) != cudaSuccess) failed = 1;
+                memcpy(slot[s], jb.host + ch.off, ch.len);
+                if (cudaMemcpyAsync(jb.dev + ch.off, slot[s], ch.len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaEventRecord(r.events[2 * t + s], st) != cudaSuccess) {
+                    failed = 1;
+                    break;
+                }
+            }
+        }
+        drain();
+        if (cudaStreamSynchronize(st) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (std::thread &th : pool) th.join();
+    if (failed) {
+        (void)cudaGetLastError();
+        set_error("streamed host copy failed");
+        return ARCTE_E_CUDA;
+    }
+    return ARCTE_OK;
+}
+
+// Device -> host.  Everything queued on the context's stream is finished first.
+int copy_to_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return ARCTE_OK;
+    if (bytes < kStreamedMin || is_pinned(dst)) {
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return ARCTE_OK;
+    }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<CopyJob> jobs{{(char *)dst, (char *)const_cast<void *>(src), bytes, true}};
+    return run_jobs(c, jobs, nullptr, 0, 0.0, 0);
+}
+
+// Host -> device; returns when the data is on the device.
+int copy_from_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return ARCTE_OK;
+    if (bytes < kStreamedMin || is_pinned(src)) {
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return ARCTE_OK;
+    }
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<CopyJob> jobs{{(char *)const_cast<void *>(src), (char *)dst, bytes, false}};
+    return run_jobs(c, jobs, nullptr, 0, 0.0, 0);
+}
+
+// The assembled feature block to the host in one pass of the thread pool: row pointers and column indices
+// are copied; the values are copied too, or -- when the caller knows they are structural (all 1.0 except
+// the self-loop diagonals it patches itself, arcte.py:379-381, :676-679) -- written as ones by the same
+// threads while the indices stream in, which saves two thirds of the PCIe bytes.
+int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data, int values_are_ones,
+                   int n_threads)
+{
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<CopyJob> jobs;
+    const size_t nnz = (size_t)c->out_nnz;
+    if (host_indptr) jobs.push_back({(char *)host_indptr, c->out_indptr.as<char>(), sizeof(int64_t) * (size_t)(c->out_rows + 1), true});
+    if (host_indices && nnz) jobs.push_back({(char *)host_indices, c->out_indices.as<char>(), sizeof(int32_t) * nnz, true});
+    double *fill = nullptr;
+    if (host_data && nnz) {
+        if (values_are_ones) fill = host_data;
+        else jobs.push_back({(char *)host_data, c->out_data.as<char>(), sizeof(double) * nnz, true});
+    }
+    return run_jobs(c, jobs, fill, fill ? nnz : 0, 1.0, n_threads);
+}
+
+}  // namespace arcte

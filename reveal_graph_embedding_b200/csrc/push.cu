@@ -538,6 +538,27 @@ static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64
     return ARCTE_OK;
 }
 
+// The pools of the dense FIFO / frontier engines and of the batched engines are each sized for most of the
+// free memory: when an extraction switches engine, the pool of the other family goes first.
+static void release_other_pools(arcte_cuda_ctx *c, bool batched, int engine)
+{
+    if (batched) {
+        if (c->bpool.mode == engine) return;   // already laid out for this engine
+        dev_free(c->slots.sr);
+        dev_free(c->slots.touched);
+        dev_free(c->slots.queue);
+        dev_free(c->slots.frontier);
+        dev_free(c->slots.fval);
+        c->slots = SlotPool();
+    } else if (c->bpool.mode >= 0 && !(c->slots.n == c->n && c->slots.n_slots > 0)) {
+        dev_free(c->bpool.tbl);
+        dev_free(c->bpool.stage);
+        dev_free(c->bpool.clean);
+        dev_free(c->bpool.queue);
+        c->bpool = BatchedPool();
+    }
+}
+
 // Which engine of the FIFO schedule walks this call (include/arcte_cuda.h, ARCTE_ENGINE_*).
 static int resolve_engine(const arcte_cuda_ctx *c, int rule)
 {
@@ -565,6 +586,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     const int64_t S = c->n_seeds > shard_rank ? (c->n_seeds - shard_rank + shard_count - 1) / shard_count : 0;
     c->n_segments = S;
     c->n_members = 0;
+    c->shard_rank = shard_rank;
+    c->shard_count = shard_count;
     c->have_segments = false;
     c->have_features = false;
     arcte_cuda_stats &stt = c->stats;
@@ -612,6 +635,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     int64_t n_slots = 0, qcap = 0;
     const int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
     const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
+    release_other_pools(c, batched, engine);
     if (frontier) {
         ARCTE_TRY(frontier_plan_slots(c, S, &n_slots));
         ARCTE_TRY(frontier_ensure_slots(c, n_slots));
@@ -779,7 +803,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
 
     if (getenv("ARCTE_CUDA_PROFILE")) {  // per-phase clock sums of instrumented kernel builds
         fprintf(stderr, "[arcte] profile counters:");
-        for (int k = PC_PROF0; k <= PC_PROF9; ++k) fprintf(stderr, " %lld", (long long)hc[k]);
+        for (int k = PC_PROF0; k <= PC_PROF19; ++k) fprintf(stderr, " %lld", (long long)hc[k]);
         fprintf(stderr, "\n");
     }
     stt.pushes = hc[PC_PUSHES];
@@ -829,6 +853,7 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
         if (!pools_ready) {
             int64_t n_slots = 0, qcap = 0;
+            if (attempt == 0) release_other_pools(c, batched, engine);
             if (frontier) {
                 ARCTE_TRY(frontier_plan_slots(c, 1, &n_slots));
                 ARCTE_TRY(frontier_ensure_slots(c, n_slots));
@@ -861,7 +886,7 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.debug_keep = 1;
         fill_rule_constants(P, rho);
         double inv_scale = 0.0;
-        const bool hash = batched && engine == ARCTE_ENGINE_BATCHED_HASH;
+        const bool hash = batched;   // both batched engines write the dense vectors themselves and clean up
         if (frontier) {
             P.scale = frontier_scale(rho);
             P.inv_scale = inv_scale = 1.0 / P.scale;

@@ -9,9 +9,11 @@
 
 namespace arcte {
 
-// Walk-state entry of the hash engine: ONE 32-byte sector per touched node, read and written with
+// Walk-state entry of the batched engines: ONE 32-byte sector per touched node, read and written with
 // single 256-bit accesses.  d_in rides along so that neither the enqueue test of a re-touch nor the
-// threshold sweep has to gather the node record again.
+// threshold sweep has to gather the node record again.  `key` is the node id in a hash table
+// (kEmptyKey when free) and the walk's epoch in the direct-mapped layout (entry v belongs to node v and
+// is valid only when its epoch is the current walk's: nothing is ever reset).
 struct __align__(32) TableEntry {
     double s, r, d_in;
     int32_t key;   // node id, kEmptyKey when free
@@ -63,6 +65,7 @@ struct PushParams {
     int64_t tbl_cap_max;       // entries per half, power of two
     int32_t *tbl_clean;        // [n_slots][2] entries of each half known to be all-EMPTY from index 0
     double *dbg_s, *dbg_r;     // operator seam: dense s / r of the single walked seed (pre-zeroed)
+    const double *edge_din;    // [nnz] in-degree of the target of every stored entry
     int uniform_rows;          // 1: every row of w holds one repeated value, kept in row_w
     const double *row_w;       // [n] that value (uniform_rows)
 };

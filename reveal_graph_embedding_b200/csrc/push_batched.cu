@@ -44,26 +44,42 @@ namespace arcte {
 
 constexpr int kU = 2;                // edge slots per lane
 constexpr int kE = 32 * kU;          // stored entries per batch
-constexpr int kCacheSlots = 256;     // shared-memory node cache per warp (<= 96 nodes per batch live in it)
+constexpr int kCacheSlots = 128;     // shared-memory node cache per warp (<= 96 distinct nodes per batch)
 constexpr int kWarpsPerCta = 4;
-constexpr int kStage = 256;          // stored entries per cp.async stage of a hub row
+constexpr int kStage = 64;           // stored entries per cp.async stage of a hub row
 constexpr int kInitLg = 10;          // a walk's table starts at 1024 entries
-constexpr int kGrowLg = 2;           // and grows fourfold
+constexpr int kGrowLg = 1;           // and doubles on demand
+static_assert(kU == 2, "edge-slot masks are 64 bits wide");
 
-struct WarpShared {
-    double2 cval[kCacheSlots];       // {s, r} of the cached node
-    double cdin[kCacheSlots];        // its in-degree
-    int32_t ckey[kCacheSlots];       // node id or -1
-    int32_t epre[33];                // exclusive prefix of the batch entries' row lengths
-    int32_t eu[32];                  // batch entries: node
-    uint32_t ebeg[32];               //                row begin
-    int32_t eq[32];                  //                cache slot
-    double erw[32];                  //                row weight (uniform rows)
-    unsigned long long stat[2][WS_COUNT];  // [0] totals of finished seeds, [1] the seed being walked
+// Per-warp shared memory.  The node cache of a batch maps a node to its references: which edge slots add
+// to it (cref) and which batch entry it is (centry); `contrib` holds the addend of every edge slot whose
+// node has more than one reference.  A hub row is staged over the same bytes (the cache is empty then).
+struct BatchShared {
+    unsigned long long cref[kCacheSlots];
+    uint32_t centry[kCacheSlots];
+    double contrib[kE];
 };
-// hub-row staging reuses the value arrays of the node cache
-static_assert(2 * kStage * sizeof(int32_t) <= sizeof(double) * kCacheSlots, "stage ids fit cdin");
-static_assert(2 * kStage * sizeof(double) <= sizeof(double2) * kCacheSlots, "stage weights fit cval");
+struct StageShared {
+    int32_t idx[2][kStage];
+    double w[2][kStage];
+    double din[2][kStage];
+};
+struct WarpShared {
+    union {
+        BatchShared b;
+        StageShared s;
+    } u;
+    int32_t ckey[kCacheSlots];       // node id or -1
+    unsigned long long enqmask;      // edge slots that enqueue, from the multi-reference nodes
+    int32_t epre[33];                // exclusive prefix of the batch entries' row lengths
+    uint32_t ebeg[32];               // batch entries: row begin
+    double erw[32];                  //                row weight (uniform rows)
+    unsigned long long stat[WS_COUNT];   // totals of the finished seeds
+};
+// the hub-row stage overwrites cref, centry (re-zeroed afterwards) and contrib (needs no reset)
+
+__device__ __forceinline__ unsigned long long below64(int x) { return x >= 64 ? ~0ull : (x <= 0 ? 0ull : ((1ull << x) - 1ull)); }
+__device__ __forceinline__ unsigned below32(int x) { return x >= 32 ? 0xffffffffu : (x <= 0 ? 0u : ((1u << x) - 1u)); }
 
 // ---- 256-bit table accesses (one sector per entry), L2-coherent --------------------------------------
 __device__ __forceinline__ TableEntry ld_entry(const TableEntry *p)
@@ -121,7 +137,7 @@ __device__ __forceinline__ bool table_find(const TableEntry *T, int lg, int v, T
 // ---- per-warp shared-memory node cache ----------------------------------------------------------------
 __device__ __forceinline__ int cache_insert(int32_t *ckey, int v, bool &owner)
 {
-    unsigned h = ((unsigned)v * 0x9E3779B1u) >> 24;
+    unsigned h = ((unsigned)v * 0x9E3779B1u) >> 25;
     for (;;) {
         const int old = atomicCAS(&ckey[h], -1, v);
         if (old == -1) { owner = true; return (int)h; }
@@ -132,9 +148,9 @@ __device__ __forceinline__ int cache_insert(int32_t *ckey, int v, bool &owner)
 
 // Walk state of one slot.
 struct Slot {
-    // dense
-    double2 *sr;
-    int32_t *touched;   // dense: touched list; hash: member staging list
+    // direct-mapped: T[v] is node v's entry, valid when its key is `epoch`
+    int32_t epoch;
+    int32_t *touched;   // direct: touched list (then the members); hash: member staging list
     // hash
     TableEntry *half[2];
     int32_t clean[2];   // entries of each half known EMPTY from 0
@@ -197,25 +213,100 @@ __device__ void table_clear(Slot &S, int lane)
     __syncwarp();
 }
 
+// Phase profile (-DARCTE_BATCH_PROFILE, ARCTE_CUDA_PROFILE=1 prints it): clock64 sums of lane 0 per phase.
+#ifdef ARCTE_BATCH_PROFILE
+#define PROF_DECL long long prof_t = clock64(); long long prof_acc[20] = {0}
+#define PROF(i) do { const long long t_ = clock64(); prof_acc[i] += t_ - prof_t; prof_t = t_; } while (0)
+#define PROF_ADD(i, v) do { prof_acc[i] += (v); } while (0)
+#define PROF_FLUSH() do { if (lane == 0) for (int i_ = 0; i_ < 20; ++i_) if (prof_acc[i_]) atomicAdd(&P.counters[PC_PROF0 + i_], (unsigned long long)prof_acc[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_ADD(i, v)
+#define PROF_FLUSH()
+#endif
+
 enum WalkResult { WALK_OK = 0, WALK_RING_OVERFLOW = 1, WALK_TABLE_OVERFLOW = 2 };
+
+// Counters of the walk in progress (warp-uniform registers; added to the warp's totals when the seed is done).
+struct WalkStat {
+    unsigned long long pushes, edges, enq;
+    unsigned maxq;
+};
+
+// `x / d >= t` as the reference evaluates it (one IEEE division, similarity.py:204, :214; arcte.py:363-367)
+// without paying for the fp64 division when a single-precision quotient already decides: the float quotient
+// is within 4e-7 of the true one (normal operands), the guard band is 1e-5, and everything inside the band,
+// denormal or out of float range goes through the exact division.  Same truth value, always.
+struct Threshold {
+    double t;
+    float lo, hi;
+};
+__device__ __forceinline__ Threshold make_threshold(double t)
+{
+    Threshold th;
+    th.t = t;
+    th.lo = __double2float_rd(t * (1.0 - 1e-5));
+    th.hi = __double2float_ru(t * (1.0 + 1e-5));
+    return th;
+}
+__device__ __forceinline__ bool quot_ge(double x, double d, const Threshold &th)
+{
+#ifndef ARCTE_NO_QUOT_FILTER
+    const float xf = __double2float_rn(x), df = __double2float_rn(d);
+    if (xf >= 1.17549435e-38f && df >= 1.17549435e-38f) {
+        const float q = __fdividef(xf, df);
+        if (q > th.hi) return true;
+        if (q < th.lo && q > 0.0f) return false;
+    }
+#endif
+    return __ddiv_rn(x, d) >= th.t;
+}
+
+// Hash engine: the state of node v for a push that is about to add to it.  The probe of the home entry and
+// the claim of a free entry (compare-and-swap on the key: lanes of the warp insert DISTINCT nodes at the
+// same time) are issued together, so a touch is one memory round trip whether the node is new or not; only
+// a collision costs another one.  (The in-degree a new entry needs arrives with the edge, PushParams::edge_din.)
+// Direct-mapped engine: entry v IS node v's, valid when tagged with the walk's epoch.
+__device__ __forceinline__ void direct_touch(const TableEntry *T, int epoch, int v, double &s, double &r, bool &is_new)
+{
+    const TableEntry e = ld_entry(T + v);
+    is_new = e.key != epoch;
+    s = is_new ? 0.0 : e.s;
+    r = is_new ? 0.0 : e.r;
+}
+__device__ __forceinline__ unsigned table_touch(TableEntry *T, int lg, int v, double &s, double &r, bool &is_new)
+{
+    const unsigned mask = (1u << lg) - 1u;
+    unsigned h = table_hash(v, lg);
+    TableEntry e = ld_entry(T + h);
+    int old = atomicCAS(&T[h].key, kEmptyKey, v);
+    for (;;) {
+        if (old == kEmptyKey) { s = r = 0.0; is_new = true; return h; }
+        if (old == v) {
+            if (e.key != v) e = ld_entry(T + h);   // cannot happen (the entry is complete since an earlier batch)
+            s = e.s; r = e.r; is_new = false; return h;
+        }
+        h = (h + 1) & mask;
+        e = ld_entry(T + h);
+        old = atomicCAS(&T[h].key, kEmptyKey, v);
+    }
+}
 
 // A row longer than kE, pushed alone (similarity.py:204-216 for one queue entry).  Column indices and
 // weights are staged through shared memory with cp.async, kStage stored entries per stage, the next
-// stage in flight while the current one is applied.
+// stage in flight while the current one is applied.  The caller has popped the entry.
 template <bool HASH>
-__device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, const NodeInfo iu, double row_w,
-                            double eps, bool first, unsigned &head, unsigned &tail, int lane, unsigned lt)
+__device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, WalkStat &ws, int u, const NodeInfo iu, double row_w,
+                            const Threshold &eps, bool first, unsigned head, unsigned &tail, int lane, unsigned lt)
 {
-    unsigned long long *ws = W.stat[1];
     const unsigned qmask = (unsigned)P.queue_cap - 1u;
     const unsigned len = iu.len;
     // state of u
-    double su_s, su_r, din_u = iu.d_in;
+    double su_s, su_r;
+    const double din_u = iu.d_in;
     unsigned tu = 0;
     if (HASH) {
-        if (S.nt + (int)min(len, (unsigned)P.n) + 1 > table_limit(S.lg)) {
-            if (!table_grow(S, S.nt + (int)min(len, (unsigned)P.n) + 1, lane)) return WALK_TABLE_OVERFLOW;
-        }
         TableEntry e;
         e.s = e.r = 0.0;
         if (lane == 0) table_find(S.T, S.lg, u, e, tu);   // u was enqueued, so it is in the table
@@ -223,26 +314,36 @@ __device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, 
         su_r = __shfl_sync(kFull, e.r, 0);
         tu = __shfl_sync(kFull, tu, 0);
     } else {
-        const double2 v = ld_state(&S.sr[u]);
-        su_s = v.x;
-        su_r = v.y;
+        const TableEntry e = ld_entry(S.T + u);   // queue entries carry the walk's epoch
+        su_s = e.s;
+        su_r = e.r;
     }
-    head += 1;
-    if (!(first || __ddiv_rn(su_r, din_u) >= eps)) return WALK_OK;  // similarity.py:204
+    if (!(first || quot_ge(su_r, din_u, eps))) return WALK_OK;  // similarity.py:204
+    if (HASH) {
+        const int need = S.nt + (int)min(len, (unsigned)P.n) + 1;
+        if (need > table_limit(S.lg)) {
+            if (!table_grow(S, need, lane)) return WALK_TABLE_OVERFLOW;
+            TableEntry e;
+            if (lane == 0) table_find(S.T, S.lg, u, e, tu);   // the table moved
+            tu = __shfl_sync(kFull, tu, 0);
+        }
+    }
     const double c = __dmul_rn(P.one_minus_rho, su_r);               // push.py:57
     if (lane == 0) {                                                 // push.py:60
         if (HASH) st_entry(S.T + tu, su_s, 0.0, din_u, u);
-        else st_state(&S.sr[u], make_double2(su_s, 0.0));
-        ws[WS_PUSHES] += 1;
-        ws[WS_EDGES] += len;
+        else st_entry(S.T + u, su_s, 0.0, din_u, S.epoch);
     }
+    ws.pushes += 1;
+    ws.edges += len;
     __syncwarp();
 
-    // staging buffers over the node cache, which is empty between batches (its keys are not touched)
-    int32_t *sidx = reinterpret_cast<int32_t *>(W.cdin);    // [2][kStage] ints  = the 2 KB of cdin
-    double *swgt = reinterpret_cast<double *>(W.cval);      // [2][kStage] doubles = the 4 KB of cval
+    // staging buffers over the reference masks of the node cache, which is empty between batches
+    int32_t *sidx = &W.u.s.idx[0][0];
+    double *swgt = &W.u.s.w[0][0];
+    double *sdin = &W.u.s.din[0][0];
     const int32_t *gidx = P.indices + iu.begin;
     const double *gw = P.w + iu.begin;
+    const double *gdin = P.edge_din + iu.begin;
     const bool uni = P.uniform_rows != 0;
     auto issue = [&](unsigned base, int buf) {
         for (int k = lane; k < kStage; k += 32) {
@@ -250,6 +351,8 @@ __device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, 
             if (j < len) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(&sidx[buf * kStage + k]);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gidx + j) : "memory");
+                const unsigned sc = (unsigned)__cvta_generic_to_shared(&sdin[buf * kStage + k]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sc), "l"(gdin + j) : "memory");
                 if (!uni) {
                     const unsigned sb = (unsigned)__cvta_generic_to_shared(&swgt[buf * kStage + k]);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb), "l"(gw + j) : "memory");
@@ -272,61 +375,37 @@ __device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, 
         const unsigned stage_n = min((unsigned)kStage, len - base);
         for (unsigned b2 = 0; b2 < stage_n; b2 += 32 * kU) {
             int v[kU];
-            double p[kU];
+            double p[kU], dv[kU];
 #pragma unroll
             for (int k = 0; k < kU; ++k) {
                 const unsigned j = b2 + k * 32 + lane;
                 v[k] = -1;
+                dv[k] = 1.0;
                 if (j < stage_n) {
                     v[k] = sidx[buf * kStage + j];
+                    dv[k] = sdin[buf * kStage + j];
                     p[k] = __dmul_rn(c, uni ? row_w : swgt[buf * kStage + j]);
                 }
             }
-            double os[kU], orr[kU], dv[kU];
+            double os[kU], orr[kU];
             unsigned tk[kU];
             unsigned f_new = 0, f_enq = 0;
-            if (HASH) {
-                TableEntry e0[kU];
 #pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if (v[k] >= 0) e0[k] = ld_entry(S.T + table_hash(v[k], S.lg));
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if (v[k] >= 0) {
-                        TableEntry e;
-                        bool is_new;
-                        tk[k] = table_find_or_insert(S.T, S.lg, v[k], e0[k], e, is_new);
-                        if (is_new) {
-                            os[k] = orr[k] = 0.0;
-                            dv[k] = ld_info_din(&P.info[v[k]]);
-                            f_new |= 1u << k;
-                        } else {
-                            os[k] = e.s;
-                            orr[k] = e.r;
-                            dv[k] = e.d_in;
-                        }
-                    }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if (v[k] >= 0) {
-                        const double2 o = ld_state(&S.sr[v[k]]);
-                        os[k] = o.x;
-                        orr[k] = o.y;
-                        dv[k] = ld_info_din(&P.info[v[k]]);
-                    }
-            }
+            for (int k = 0; k < kU; ++k)
+                if (v[k] >= 0) {
+                    bool is_new;
+                    if (HASH) tk[k] = table_touch(S.T, S.lg, v[k], os[k], orr[k], is_new);
+                    else direct_touch(S.T, S.epoch, v[k], os[k], orr[k], is_new);
+                    if (is_new) f_new |= 1u << k;
+                }
 #pragma unroll
             for (int k = 0; k < kU; ++k)
                 if (v[k] >= 0) {
                     const double ns = __dadd_rn(os[k], p[k]);   // push.py:63
                     const double nr = __dadd_rn(orr[k], p[k]);  // push.py:64
                     if (HASH) st_entry(S.T + tk[k], ns, nr, dv[k], v[k]);
-                    else {
-                        st_state(&S.sr[v[k]], make_double2(ns, nr));
-                        if ((os[k] == 0.0 && orr[k] == 0.0) && (ns != 0.0 || nr != 0.0)) f_new |= 1u << k;
-                    }
-                    if (__ddiv_rn(nr, dv[k]) >= eps) f_enq |= 1u << k;  // similarity.py:214
+                    else st_entry(S.T + v[k], ns, nr, dv[k], S.epoch);
+                    if (quot_ge(nr, dv[k], eps)) f_enq |= 1u << k;  // similarity.py:214
                 }
             // ordered appends: stored-entry order = chunk order, then lane order
 #pragma unroll
@@ -347,7 +426,7 @@ __device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, 
                     if (tail - head + cnt > (unsigned)P.queue_cap) { result = WALK_RING_OVERFLOW; break; }
                     if (enq) S.queue[(tail + __popc(m_enq & lt)) & qmask] = v[k];
                     tail += cnt;
-                    if (lane == 0) ws[WS_ENQ] += cnt;
+                    ws.enq += cnt;
                 }
             }
             if (result != WALK_OK) break;
@@ -356,13 +435,21 @@ __device__ int push_hub_row(const PushParams &P, WarpShared &W, Slot &S, int u, 
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    if (lane == 0 && tail - head > ws[WS_MAXQ]) ws[WS_MAXQ] = tail - head;
+    for (int i = lane; i < kCacheSlots; i += 32) {   // the reference masks again, all clear
+        W.u.b.cref[i] = 0ull;
+        W.u.b.centry[i] = 0u;
+    }
     __syncwarp();
+    if (tail - head > ws.maxq) ws.maxq = tail - head;
     return result;
 }
 
+#ifndef ARCTE_BATCH_MIN_CTAS
+#define ARCTE_BATCH_MIN_CTAS 4
+#endif
+
 template <bool HASH>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 4)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, ARCTE_BATCH_MIN_CTAS)
 k_walk_batched(const PushParams P)
 {
     __shared__ WarpShared wsm[kWarpsPerCta];
@@ -372,9 +459,12 @@ k_walk_batched(const PushParams P)
     const int64_t slot = (int64_t)blockIdx.x * kWarpsPerCta + wib;
     if (slot >= P.n_slots) return;
     WarpShared &W = wsm[wib];
-    unsigned long long *wtot = W.stat[0];
-    unsigned long long *ws = W.stat[1];
-    for (int i = lane; i < kCacheSlots; i += 32) W.ckey[i] = -1;
+    unsigned long long *wtot = W.stat;
+    for (int i = lane; i < kCacheSlots; i += 32) {
+        W.ckey[i] = -1;
+        W.u.b.cref[i] = 0ull;
+        W.u.b.centry[i] = 0u;
+    }
     if (lane < WS_COUNT) wtot[lane] = 0ull;
     __syncwarp();
     if (lane == 0) {
@@ -386,7 +476,7 @@ k_walk_batched(const PushParams P)
     Slot S;
     S.queue = P.queue + slot * P.queue_cap;
     S.touched = P.touched + slot * P.touched_stride;
-    S.sr = nullptr;
+    S.epoch = 0;
     S.half[0] = S.half[1] = S.T = nullptr;
     S.clean[0] = S.clean[1] = 0;
     S.cur = 0;
@@ -399,10 +489,12 @@ k_walk_batched(const PushParams P)
         S.clean[0] = P.tbl_clean[slot * 2 + 0];
         S.clean[1] = P.tbl_clean[slot * 2 + 1];
     } else {
-        S.sr = P.sr + slot * P.n;
+        S.T = P.tbl + slot * P.tbl_cap_max;     // one entry per node
+        S.epoch = P.tbl_clean[slot * 2 + 0];    // last epoch this slot used (0 = none: the pool starts zeroed)
     }
     const unsigned qmask = (unsigned)P.queue_cap - 1u;
     const bool uni = P.uniform_rows != 0;
+    PROF_DECL;
 
     for (;;) {
         unsigned long long wk = 0;
@@ -411,9 +503,11 @@ k_walk_batched(const PushParams P)
         if ((int64_t)wk >= P.n_work) break;
         const int pos = P.work_ids ? P.work_ids[wk] : (int)wk;
         const int seed = P.work_seed[pos];
-        const double eps = P.work_eps[pos];
+        const Threshold eps = make_threshold(P.work_eps[pos]);
         const NodeInfo si = P.info[seed];
-        if (lane < WS_COUNT) ws[lane] = 0ull;
+        WalkStat ws;
+        ws.pushes = ws.edges = ws.enq = 0ull;
+        ws.maxq = 0u;
 
         // ---- initial state: s[seed] = r[seed] = 1 (similarity.py:176-177), queue = [seed] ----
         if (HASH) {
@@ -424,9 +518,12 @@ k_walk_batched(const PushParams P)
             S.T = S.half[0];
             table_make_clean(S, 0, lg0, lane);
             if (lane == 0) st_entry(S.T + table_hash(seed, lg0), 1.0, 1.0, si.d_in, seed);
-        } else if (lane == 0) {
-            st_state(&S.sr[seed], make_double2(1.0, 1.0));
-            S.touched[0] = seed;
+        } else {
+            S.epoch += 1;   // every entry of the previous walk (finished or aborted) is stale from here on
+            if (lane == 0) {
+                st_entry(S.T + seed, 1.0, 1.0, si.d_in, S.epoch);
+                S.touched[0] = seed;
+            }
         }
         S.nt = 1;
         if (lane == 0) S.queue[0] = seed;
@@ -435,66 +532,78 @@ k_walk_batched(const PushParams P)
         unsigned head = 0, tail = 1;
         bool first = true;   // "Do one push for free", similarity.py:183-196
         int result = WALK_OK;
+        // Queue entries already in registers: lane i holds the entry at queue position head + i (node, node
+        // record, row weight) for i < n_main.  Entries a batch does not consume stay (shifted down), and the
+        // ones behind them are fetched while the batch is in flight: every node record is read once.
+        int eu = -1;
+        double ed = 1.0, erw = 0.0;
+        unsigned eb = 0, el = 0;
+        int n_main = 0;
+        PROF(8);
 
         while (head != tail && result == WALK_OK) {
-            // ---- the batch: consecutive queue entries whose rows fit kE edge slots ----
             const unsigned avail = tail - head;
-            const int B0 = avail < 32u ? (int)avail : 32;
-            int u = -1;
-            NodeInfo iu;
-            iu.d_in = 1.0;
-            iu.begin = 0;
-            iu.len = 0;
-            double rw = 0.0;
-            if (lane < B0) {
-                u = S.queue[(head + lane) & qmask];
-                iu = ld_info(&P.info[u]);
-                if (uni) rw = P.row_w[u];
+            const int want = avail < 32u ? (int)avail : 32;
+            const bool first_in = first;
+            // ---- (A) queue entries not yet in registers: node ids now, node records a little later ----
+            const bool incoming = lane >= n_main && lane < want;
+            const int n_main0 = n_main;
+            int nu = -1;
+            double nd = 1.0, nrw = 0.0;
+            unsigned nb = 0, nl = 0;
+            if (incoming) nu = S.queue[(head + lane) & qmask];
+            if (n_main0 == 0) {   // nothing pre-fetched (start of a walk, or the queue ran dry): wait for them
+                if (incoming) {
+                    const NodeInfo t = ld_info(&P.info[nu]);
+                    eu = nu; ed = t.d_in; eb = t.begin; el = t.len;
+                    if (uni) erw = P.row_w[nu];
+                }
+                n_main = want;
             }
-            unsigned incl = iu.len > (unsigned)kE ? (unsigned)kE + 1u : iu.len;   // saturate: sums stay small
+            // ---- (B) the batch: leading entries whose rows fit kE edge slots; a row longer than kE takes no
+            //      slot here: only its pop check is done in the batch, the push itself (if any) on its own ----
+            const bool have = lane < n_main;
+            const bool hub = have && el > (unsigned)kE;
+            unsigned incl = have ? (hub ? 0u : el) : (unsigned)kE + 1u;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned t = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += t;
             }
-            const bool fit = lane < B0 && incl <= (unsigned)kE;
-            const int Bp = __popc(__ballot_sync(kFull, fit));   // rows are taken from the front: fit is a prefix
-            if (Bp == 0) {
-                const int u0 = __shfl_sync(kFull, u, 0);
-                NodeInfo i0;
-                i0.d_in = __shfl_sync(kFull, iu.d_in, 0);
-                i0.begin = __shfl_sync(kFull, iu.begin, 0);
-                i0.len = __shfl_sync(kFull, iu.len, 0);
-                const double rw0 = __shfl_sync(kFull, rw, 0);
-                result = push_hub_row<HASH>(P, W, S, u0, i0, rw0, eps, first, head, tail, lane, lt);
-                first = false;
-                continue;
-            }
+            const int Bp = __popc(__ballot_sync(kFull, have && incl <= (unsigned)kE));   // >= 1: fit is a prefix
             const int total = (int)__shfl_sync(kFull, incl, Bp - 1);
+            const int my_lo = (int)(incl - (hub ? 0u : el));   // first edge slot of this lane's entry (lane < Bp)
+            PROF(0);
             if (HASH && S.nt + total + 1 > table_limit(S.lg)) {
                 if (!table_grow(S, S.nt + total + 1, lane)) { result = WALK_TABLE_OVERFLOW; break; }
+                PROF(1);
+                PROF_ADD(13, 1);
             }
+            PROF_ADD(9, 1);
+            PROF_ADD(10, Bp);
+            PROF_ADD(11, total);
             if (lane < Bp) {
-                W.eu[lane] = u;
-                W.ebeg[lane] = iu.begin;
+                W.ebeg[lane] = eb;
                 W.epre[lane + 1] = (int)incl;
-                W.erw[lane] = rw;
+                W.erw[lane] = erw;
             }
-            if (lane == 0) W.epre[0] = 0;
+            if (lane == 0) {
+                W.epre[0] = 0;
+                W.enqmask = 0ull;
+            }
             __syncwarp();
 
-            // ---- gather: neighbour ids + weights of all edge slots, then every distinct node's state ----
+            // ---- (C) neighbour ids + weights of all edge slots ----
             int vk[kU], jk[kU], qk[kU];
-            double wgt[kU];
-            unsigned tk[kU];
+            double wgt[kU], dv[kU];
 #pragma unroll
             for (int k = 0; k < kU; ++k) {
                 const int e = k * 32 + lane;
                 vk[k] = -1;
-                jk[k] = -1;
+                jk[k] = 0;
                 qk[k] = 0;
-                tk[k] = 0;
                 wgt[k] = 0.0;
+                dv[k] = 1.0;
                 if (e < total) {
                     int lo = 0, hi = Bp - 1;   // the entry j with epre[j] <= e < epre[j+1]
                     while (lo < hi) {
@@ -505,17 +614,24 @@ k_walk_batched(const PushParams P)
                     const unsigned at = W.ebeg[lo] + (unsigned)(e - W.epre[lo]);
                     jk[k] = lo;
                     vk[k] = ld_index(P.indices + at);
+                    dv[k] = P.edge_din[at];
                     wgt[k] = uni ? W.erw[lo] : ld_weight(P.w + at);
                 }
             }
-            unsigned own = 0, f_new = 0;   // bit k: edge slot k, bit kU: the lane's batch entry
+            // node records of the incoming queue entries (their ids have arrived by now); used next iteration
+            if (incoming && n_main0 != 0) {
+                const NodeInfo t = ld_info(&P.info[nu]);
+                nd = t.d_in; nb = t.begin; nl = t.len;
+                if (uni) nrw = P.row_w[nu];
+            }
+            // ---- (D) who references which node: cref = edge slots, centry = batch entries, per distinct node ----
+            unsigned own = 0;   // bit k: this lane's edge slot k created the cache slot, bit kU: its batch entry did
             int qe = 0;
-            unsigned te = 0;
             if (lane < Bp) {
                 bool o;
-                qe = cache_insert(W.ckey, u, o);
-                W.eq[lane] = qe;
+                qe = cache_insert(W.ckey, eu, o);
                 if (o) own |= 1u << kU;
+                atomicOr(&W.u.b.centry[qe], 1u << lane);
             }
 #pragma unroll
             for (int k = 0; k < kU; ++k)
@@ -523,146 +639,259 @@ k_walk_batched(const PushParams P)
                     bool o;
                     qk[k] = cache_insert(W.ckey, vk[k], o);
                     if (o) own |= 1u << k;
+                    atomicOr(&W.u.b.cref[qk[k]], 1ull << (k * 32 + lane));
                 }
-            if (HASH) {
-                TableEntry e0[kU + 1];
+            __syncwarp();
+            // An entry whose node is referenced EARLIER in the batch (by the row of an earlier entry, or as an
+            // earlier entry: a duplicate in the queue) needs the value those pushes leave: the batch ends before
+            // it.  Every entry that stays can then be checked and its push coefficient computed at once.
+            // A node that is simply in the queue twice with no such reference in between needs no such care: its
+            // second pop sees what the first one left (r = 0 after a push, or the same failing value) and does
+            // nothing; the first of the entries owns the node.
+            unsigned long long mref_e = 0ull;
+            bool dep = false, dupl = false;
+            if (lane < Bp) {
+                mref_e = W.u.b.cref[qe];
+                dep = (mref_e & below64(my_lo)) != 0ull;
+                dupl = (W.u.b.centry[qe] & ((1u << lane) - 1u)) != 0u;
+            }
+            const unsigned depm = __ballot_sync(kFull, dep);
+            const int j_lim = depm ? __ffs(depm) - 1 : Bp;   // >= 1
+            const int e_lim = W.epre[j_lim];
+            const unsigned long long in64 = below64(e_lim);
+            // per edge slot: the node's references inside the batch, whether an entry owns it, whether this slot leads
+            unsigned long long mref_k[kU];
+            unsigned f_in = 0, f_lead = 0, f_single = 0;
+#pragma unroll
+            for (int k = 0; k < kU; ++k) {
+                mref_k[k] = 0ull;
+                const int e = k * 32 + lane;
+                if (vk[k] >= 0 && e < e_lim) {
+                    f_in |= 1u << k;
+                    mref_k[k] = W.u.b.cref[qk[k]] & in64;
+                    const bool entry_owned = (W.u.b.centry[qk[k]] & below32(j_lim)) != 0u;   // its first entry owns it
+                    if (!entry_owned && (mref_k[k] & (0ull - mref_k[k])) == (1ull << e)) {
+                        f_lead |= 1u << k;
+                        if ((mref_k[k] & (mref_k[k] - 1ull)) == 0ull) f_single |= 1u << k;
+                    }
+                }
+            }
+            PROF(2);
+            PROF_ADD(15, j_lim < Bp ? 1 : 0);
+
+            // ---- (E) state of every distinct node, fetched by its leading reference ----
+            double os[kU], orr[kU];
+            unsigned tk[kU + 1];
+            unsigned f_new = 0;   // the node was not part of the walk yet
+            double es = 0.0, er = 0.0;
+            const bool e_owner = lane < j_lim && !dupl;   // this lane's entry is the first (or only) one of its node
+#pragma unroll
+            for (int k = 0; k <= kU; ++k) tk[k] = 0;
+#pragma unroll
+            for (int k = 0; k < kU; ++k) os[k] = orr[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < kU; ++k)
+                if ((f_lead >> k) & 1u) {
+                    bool is_new;
+                    if (HASH) tk[k] = table_touch(S.T, S.lg, vk[k], os[k], orr[k], is_new);
+                    else direct_touch(S.T, S.epoch, vk[k], os[k], orr[k], is_new);
+                    if (is_new) f_new |= 1u << k;
+                }
+            if (e_owner) {   // queue entries are part of the walk: found / tagged for sure
+                TableEntry e;
+                e.s = e.r = 0.0;
+                if (HASH) table_find(S.T, S.lg, eu, e, tk[kU]);
+                else e = ld_entry(S.T + eu);
+                es = e.s;
+                er = e.r;
+            }
+            PROF(3);
+
+            // ---- (F) pop checks of all entries (similarity.py:204); a long row that passes ends the batch ----
+            const bool pass = e_owner && ((first_in && lane == 0) || quot_ge(er, ed, eps));
+            const unsigned stopm = __ballot_sync(kFull, pass && hub);
+            const int j_stop = stopm ? __ffs(stopm) - 1 : j_lim;
+            const bool act = pass && lane < j_stop;
+            const unsigned actm = __ballot_sync(kFull, act);
+            const double c = act ? __dmul_rn(P.one_minus_rho, er) : 0.0;   // push.py:57
+            if (act) er = 0.0;                                               // push.py:60
+
+            // ---- (G) contributions; a node with one reference is finished in registers ----
+            unsigned f_act = 0, f_enq = 0;
+#pragma unroll
+            for (int k = 0; k < kU; ++k) {
+                const double ce = __shfl_sync(kFull, c, jk[k]);
+                if (((f_in >> k) & 1u) && ((actm >> jk[k]) & 1u)) {
+                    const double p = __dmul_rn(ce, wgt[k]);
+                    f_act |= 1u << k;
+                    if ((f_single >> k) & 1u) {
+                        os[k] = __dadd_rn(os[k], p);     // push.py:63
+                        orr[k] = __dadd_rn(orr[k], p);   // push.py:64
+                        if (quot_ge(orr[k], dv[k], eps)) f_enq |= 1u << k;   // similarity.py:214
+                    } else {
+                        W.u.b.contrib[k * 32 + lane] = p;
+                    }
+                }
+            }
+            unsigned long long act64 = 0ull;
+#pragma unroll
+            for (int k = 0; k < kU; ++k) act64 |= (unsigned long long)__ballot_sync(kFull, (f_act >> k) & 1u) << (32 * k);
+            const bool any_multi = __any_sync(kFull, (f_act & ~f_single) != 0u);
+            unsigned f_mod = f_act & f_single;   // leading slots whose value changed
+            bool e_mod = act;
+            if (any_multi) {
+                // ---- (H) a node with several references: its leading reference (or the entry that IS the node)
+                //      adds the contributions in edge-slot order = queue order, then CSR order ----
+                __syncwarp();
+                unsigned long long flags = 0ull;
 #pragma unroll
                 for (int k = 0; k < kU; ++k)
-                    if ((own >> k) & 1u) e0[k] = ld_entry(S.T + table_hash(vk[k], S.lg));
-                if ((own >> kU) & 1u) e0[kU] = ld_entry(S.T + table_hash(u, S.lg));
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if ((own >> k) & 1u) {
-                        TableEntry e;
-                        bool is_new;
-                        tk[k] = table_find_or_insert(S.T, S.lg, vk[k], e0[k], e, is_new);
-                        if (is_new) {
-                            W.cval[qk[k]] = make_double2(0.0, 0.0);
-                            W.cdin[qk[k]] = ld_info_din(&P.info[vk[k]]);
-                            f_new |= 1u << k;
-                        } else {
-                            W.cval[qk[k]] = make_double2(e.s, e.r);
-                            W.cdin[qk[k]] = e.d_in;
+                    if (((f_lead & ~f_single) >> k) & 1u) {
+                        unsigned long long todo = mref_k[k] & act64;
+                        while (todo) {
+                            const int e2 = __ffsll((long long)todo) - 1;
+                            todo &= todo - 1ull;
+                            const double p = W.u.b.contrib[e2];
+                            os[k] = __dadd_rn(os[k], p);
+                            orr[k] = __dadd_rn(orr[k], p);
+                            f_mod |= 1u << k;
+                            if (quot_ge(orr[k], dv[k], eps)) flags |= 1ull << e2;
                         }
                     }
-                if ((own >> kU) & 1u) {
-                    TableEntry e;
-                    bool is_new;
-                    te = table_find_or_insert(S.T, S.lg, u, e0[kU], e, is_new);   // always found: u was enqueued
-                    W.cval[qe] = is_new ? make_double2(0.0, 0.0) : make_double2(e.s, e.r);
-                    W.cdin[qe] = iu.d_in;
-                    if (is_new) f_new |= 1u << kU;
+                if (e_owner) {   // references to an entry's node all come after its pop
+                    unsigned long long todo = mref_e & in64 & act64;
+                    while (todo) {
+                        const int e2 = __ffsll((long long)todo) - 1;
+                        todo &= todo - 1ull;
+                        const double p = W.u.b.contrib[e2];
+                        es = __dadd_rn(es, p);
+                        er = __dadd_rn(er, p);
+                        e_mod = true;
+                        if (quot_ge(er, ed, eps)) flags |= 1ull << e2;
+                    }
                 }
-            } else {
-                double2 o[kU + 1];
-                double dv[kU];
+                if (flags) atomicOr(&W.enqmask, flags);
+                __syncwarp();
+                const unsigned long long em = W.enqmask;
 #pragma unroll
                 for (int k = 0; k < kU; ++k)
-                    if ((own >> k) & 1u) {
-                        o[k] = ld_state(&S.sr[vk[k]]);
-                        dv[k] = ld_info_din(&P.info[vk[k]]);
-                    }
-                if ((own >> kU) & 1u) o[kU] = ld_state(&S.sr[u]);
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if ((own >> k) & 1u) {
-                        W.cval[qk[k]] = o[k];
-                        W.cdin[qk[k]] = dv[k];
-                        if (o[k].x == 0.0 && o[k].y == 0.0) f_new |= 1u << k;   // untouched so far
-                    }
-                if ((own >> kU) & 1u) {
-                    W.cval[qe] = o[kU];
-                    W.cdin[qe] = iu.d_in;
-                }
+                    if (((f_act & ~f_single) >> k) & 1u)
+                        if ((em >> (k * 32 + lane)) & 1ull) f_enq |= 1u << k;
             }
-            __syncwarp();
+            PROF(4);
 
-            // ---- apply the pushes to the cache strictly in queue order (similarity.py:199-216) ----
-            for (int j = 0; j < Bp; ++j) {
-                const int qu = W.eq[j];
-                const double2 su = W.cval[qu];
-                const double din_u = W.cdin[qu];
-                const bool pass = first || __ddiv_rn(su.y, din_u) >= eps;   // similarity.py:204
-                first = false;
-                __syncwarp();
-                if (!pass) continue;   // warp-uniform
-                const double c = __dmul_rn(P.one_minus_rho, su.y);          // push.py:57
-                if (lane == 0) W.cval[qu] = make_double2(su.x, 0.0);         // push.py:60
-                __syncwarp();
-                unsigned f_enq = 0;
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if (jk[k] == j) {   // rows hold distinct columns: no two lanes share a cache slot here
-                        const double2 o = W.cval[qk[k]];
-                        const double p = __dmul_rn(c, wgt[k]);
-                        const double2 nw = make_double2(__dadd_rn(o.x, p), __dadd_rn(o.y, p));   // push.py:63-64
-                        W.cval[qk[k]] = nw;
-                        if (__ddiv_rn(nw.y, W.cdin[qk[k]]) >= eps) f_enq |= 1u << k;              // similarity.py:214
-                    }
-                const unsigned popped = head + (unsigned)j + 1u;
+            // ---- (I) ordered append: edge slots are numbered entry by entry, each row in CSR order ----
+            {
+                unsigned m_enq[kU];
+                unsigned cnt = 0;
 #pragma unroll
                 for (int k = 0; k < kU; ++k) {
-                    const unsigned m_enq = __ballot_sync(kFull, (f_enq >> k) & 1u);
-                    const unsigned cnt = __popc(m_enq);
-                    if (cnt) {
-                        // entries of this batch are already in shared memory: their ring cells are free
-                        if (tail - (head + (unsigned)Bp) + cnt > (unsigned)P.queue_cap) { result = WALK_RING_OVERFLOW; break; }
-                        if ((f_enq >> k) & 1u) S.queue[(tail + __popc(m_enq & lt)) & qmask] = vk[k];
-                        tail += cnt;
-                        if (lane == 0) ws[WS_ENQ] += cnt;
-                    }
+                    m_enq[k] = __ballot_sync(kFull, (f_enq >> k) & 1u);
+                    cnt += __popc(m_enq[k]);
                 }
+                if (tail - (head + (unsigned)j_stop) + cnt > (unsigned)P.queue_cap) {
+                    result = WALK_RING_OVERFLOW;
+                } else {
+                    unsigned before = 0;
+#pragma unroll
+                    for (int k = 0; k < kU; ++k) {
+                        if ((f_enq >> k) & 1u) S.queue[(tail + before + __popc(m_enq[k] & lt)) & qmask] = vk[k];
+                        before += __popc(m_enq[k]);
+                    }
+                    // counters exactly as the one-at-a-time walk would leave them
+                    ws.pushes += __popc(actm);
+                    ws.enq += cnt;
+                    unsigned elen = act ? el : 0u;
+                    unsigned qlen = 0;
+                    if (act) {   // queue length right after this entry's push
+                        const int upto = (int)incl;   // edge slots below this belong to entries <= lane
+                        unsigned cum = 0;
+#pragma unroll
+                        for (int k = 0; k < kU; ++k) cum += __popc(m_enq[k] & below32(upto - 32 * k));
+                        qlen = tail + cum - (head + (unsigned)lane + 1u);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        elen += __shfl_xor_sync(kFull, elen, o);
+                        qlen = max(qlen, __shfl_xor_sync(kFull, qlen, o));
+                    }
+                    ws.edges += elen;
+                    if (qlen > ws.maxq) ws.maxq = qlen;
+                    tail += cnt;
+                }
+            }
+            // ---- (J) write back what changed (a hash entry that was claimed but not added to is completed) ----
+            if (result == WALK_OK) {
+                if (HASH) {
+#pragma unroll
+                    for (int k = 0; k < kU; ++k)
+                        if (((f_mod | f_new) >> k) & 1u) st_entry(S.T + tk[k], os[k], orr[k], dv[k], vk[k]);
+                    if (e_mod) st_entry(S.T + tk[kU], es, er, ed, eu);
+#pragma unroll
+                    for (int k = 0; k < kU; ++k) S.nt += __popc(__ballot_sync(kFull, (f_new >> k) & 1u));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kU; ++k) {
+                        const bool wr = (f_mod >> k) & 1u;
+                        if (wr) st_entry(S.T + vk[k], os[k], orr[k], dv[k], S.epoch);
+                        const bool is_new = wr && ((f_new >> k) & 1u);   // joins the walk: listed for the sweep
+                        const unsigned m_new = __ballot_sync(kFull, is_new);
+                        if (is_new) S.touched[S.nt + __popc(m_new & lt)] = vk[k];
+                        S.nt += __popc(m_new);
+                    }
+                    if (e_mod) st_entry(S.T + eu, es, er, ed, S.epoch);
+                }
+            }
+            // ---- (K) hand the node cache back empty ----
+            if ((own >> kU) & 1u) {
+                W.ckey[qe] = -1;
+                W.u.b.cref[qe] = 0ull;
+                W.u.b.centry[qe] = 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < kU; ++k)
+                if ((own >> k) & 1u) {
+                    W.ckey[qk[k]] = -1;
+                    W.u.b.cref[qk[k]] = 0ull;
+                    W.u.b.centry[qk[k]] = 0u;
+                }
+            __syncwarp();
+            PROF(5);
+            if (result != WALK_OK) break;
+            const bool hub_is_first = first_in && j_stop == 0;   // the seed itself has a long row
+            first = false;
+
+            int consumed = j_stop;
+            head += (unsigned)j_stop;
+            if (stopm) {
+                // the entry at j_stop is a long row whose pop check passed: push it now, alone
+                const int u0 = __shfl_sync(kFull, eu, j_stop);
+                NodeInfo i0;
+                i0.d_in = __shfl_sync(kFull, ed, j_stop);
+                i0.begin = __shfl_sync(kFull, eb, j_stop);
+                i0.len = __shfl_sync(kFull, el, j_stop);
+                const double rw0 = __shfl_sync(kFull, erw, j_stop);
+                head += 1u;
+                consumed += 1;
+                result = push_hub_row<HASH>(P, W, S, ws, u0, i0, rw0, eps, hub_is_first, head, tail, lane, lt);
+                PROF(6);
+                PROF_ADD(14, 1);
                 if (result != WALK_OK) break;
-                if (lane == 0) {
-                    ws[WS_PUSHES] += 1;
-                    ws[WS_EDGES] += (unsigned)(W.epre[j + 1] - W.epre[j]);
-                    if (tail - popped > ws[WS_MAXQ]) ws[WS_MAXQ] = tail - popped;
-                }
-                __syncwarp();
             }
-            if (result != WALK_OK) {
-                for (int i = lane; i < kCacheSlots; i += 32) W.ckey[i] = -1;
-                __syncwarp();
-                break;
+            // ---- shift the entries that were not consumed to the front, append the incoming ones ----
+            {
+                const int n_keep = n_main - consumed;            // >= 0
+                const int n_inc = n_main0 == 0 ? 0 : want - n_main0;
+                const int d = consumed & 31;
+                const int t_u = __shfl_down_sync(kFull, eu, d), t_nu = __shfl_down_sync(kFull, nu, d);
+                const double t_d = __shfl_down_sync(kFull, ed, d), t_nd = __shfl_down_sync(kFull, nd, d);
+                const double t_w = __shfl_down_sync(kFull, erw, d), t_nw = __shfl_down_sync(kFull, nrw, d);
+                const unsigned t_b = __shfl_down_sync(kFull, eb, d), t_nb = __shfl_down_sync(kFull, nb, d);
+                const unsigned t_l = __shfl_down_sync(kFull, el, d), t_nl = __shfl_down_sync(kFull, nl, d);
+                if (lane < n_keep) { eu = t_u; ed = t_d; erw = t_w; eb = t_b; el = t_l; }
+                else if (lane < n_keep + n_inc) { eu = t_nu; ed = t_nd; erw = t_nw; eb = t_nb; el = t_nl; }
+                n_main = n_keep + n_inc;
             }
-
-            // ---- write the cache back, one store per distinct node ----
-            if (HASH) {
-#pragma unroll
-                for (int k = 0; k < kU; ++k)
-                    if ((own >> k) & 1u) {
-                        const double2 nv = W.cval[qk[k]];
-                        st_entry(S.T + tk[k], nv.x, nv.y, W.cdin[qk[k]], vk[k]);
-                        W.ckey[qk[k]] = -1;
-                    }
-                if ((own >> kU) & 1u) {
-                    const double2 nv = W.cval[qe];
-                    st_entry(S.T + te, nv.x, nv.y, iu.d_in, u);
-                    W.ckey[qe] = -1;
-                }
-#pragma unroll
-                for (int k = 0; k <= kU; ++k) S.nt += __popc(__ballot_sync(kFull, (f_new >> k) & 1u));
-            } else {
-#pragma unroll
-                for (int k = 0; k < kU; ++k) {
-                    bool is_new = false;
-                    if ((own >> k) & 1u) {
-                        const double2 nv = W.cval[qk[k]];
-                        st_state(&S.sr[vk[k]], nv);
-                        W.ckey[qk[k]] = -1;
-                        is_new = ((f_new >> k) & 1u) && (nv.x != 0.0 || nv.y != 0.0);
-                    }
-                    const unsigned m_new = __ballot_sync(kFull, is_new);
-                    if (is_new) S.touched[S.nt + __popc(m_new & lt)] = vk[k];
-                    S.nt += __popc(m_new);
-                }
-                if ((own >> kU) & 1u) {
-                    st_state(&S.sr[u], W.cval[qe]);
-                    W.ckey[qe] = -1;
-                }
-            }
-            __syncwarp();
-            head += (unsigned)Bp;
         }
 
         if (P.debug_keep) {   // operator seam: dense s and r of this one walk
@@ -678,9 +907,17 @@ k_walk_batched(const PushParams P)
                         S.T[i].key = kEmptyKey;
                     }
                 }
+            } else if (result == WALK_OK) {
+                __syncwarp();
+                for (int i = lane; i < S.nt; i += 32) {
+                    const int x = S.touched[i];
+                    const TableEntry e = ld_entry(S.T + x);
+                    P.dbg_s[x] = e.s;
+                    P.dbg_r[x] = e.r;
+                }
             }
             if (lane == 0) {
-                P.counters[PC_PUSHES] = ws[WS_PUSHES];
+                P.counters[PC_PUSHES] = ws.pushes;
                 P.counters[PC_TOUCHED] = (unsigned long long)S.nt;
                 P.counters[PC_OVERFLOW_SEEDS] = result == WALK_OK ? 0ull : 1ull;
                 if (result == WALK_TABLE_OVERFLOW) P.counters[PC_TOVERFLOW] = 1ull;
@@ -690,11 +927,12 @@ k_walk_batched(const PushParams P)
 
         if (result != WALK_OK) {
             // undo and hand the seed to the retry pass
-            if (HASH) table_clear(S, lane);
-            else {
-                __syncwarp();
-                for (int i = lane; i < S.nt; i += 32) st_state(&S.sr[S.touched[i]], make_double2(0.0, 0.0));
+            for (int i = lane; i < kCacheSlots; i += 32) {
+                W.ckey[i] = -1;
+                W.u.b.cref[i] = 0ull;
+                W.u.b.centry[i] = 0u;
             }
+            if (HASH) table_clear(S, lane);   // (direct-mapped: the next walk's epoch makes these entries stale)
             if (lane == 0) {
                 const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
                 P.retry_list[r] = pos;
@@ -728,18 +966,18 @@ k_walk_batched(const PushParams P)
                     else q = fmin(q, __ddiv_rn(0.0, ld_info_din(&P.info[v])));
                 }
             }
-            const double tau = warp_min(q);
+            const Threshold tau = make_threshold(warp_min(q));
             // one linear scan: support count, members (ties included, arcte.py:363-367), table reset
             const int C = 1 << S.lg;
-            for (int i0 = 0; i0 < C; i0 += 64) {
-                TableEntry e[2];
+            for (int i0 = 0; i0 < C; i0 += 128) {
+                TableEntry e[4];
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) e[k2] = ld_entry(S.T + i0 + k2 * 32 + lane);   // C >= 1024: in range
+                for (int k2 = 0; k2 < 4; ++k2) e[k2] = ld_entry(S.T + i0 + k2 * 32 + lane);   // C >= 1024: in range
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
+                for (int k2 = 0; k2 < 4; ++k2) {
                     const bool occ = e[k2].key != kEmptyKey;
                     const bool in_sup = occ && e[k2].s != 0.0;
-                    const bool pass = in_sup && (__ddiv_rn(e[k2].s, e[k2].d_in) >= tau);
+                    const bool pass = in_sup && quot_ge(e[k2].s, e[k2].d_in, tau);
                     if (occ) S.T[i0 + k2 * 32 + lane].key = kEmptyKey;
                     support += __popc(__ballot_sync(kFull, in_sup));
                     const unsigned mp = __ballot_sync(kFull, pass);
@@ -748,11 +986,11 @@ k_walk_batched(const PushParams P)
                 }
             }
         } else {
-            q = __ddiv_rn(ld_state(&S.sr[seed]).x, si.d_in);
+            // every node of N(seed) + seed was tagged by the seed's own push
+            q = __ddiv_rn(ld_entry(S.T + seed).s, si.d_in);
             for (unsigned j0 = 0; j0 < si.len; j0 += 64) {
                 int v[2];
-                double2 o[2];
-                double d[2];
+                TableEntry o[2];
 #pragma unroll
                 for (int k2 = 0; k2 < 2; ++k2) {
                     const unsigned j = j0 + k2 * 32 + lane;
@@ -760,38 +998,35 @@ k_walk_batched(const PushParams P)
                 }
 #pragma unroll
                 for (int k2 = 0; k2 < 2; ++k2)
-                    if (v[k2] >= 0) {
-                        o[k2] = ld_state(&S.sr[v[k2]]);
-                        d[k2] = ld_info_din(&P.info[v[k2]]);
-                    }
+                    if (v[k2] >= 0) o[k2] = ld_entry(S.T + v[k2]);
 #pragma unroll
                 for (int k2 = 0; k2 < 2; ++k2)
-                    if (v[k2] >= 0) q = fmin(q, __ddiv_rn(o[k2].x, d[k2]));   // arcte.py:355-356
+                    if (v[k2] >= 0) {
+                        if (o[k2].key == S.epoch) q = fmin(q, __ddiv_rn(o[k2].s, o[k2].d_in));   // arcte.py:355-356
+                        else q = fmin(q, __ddiv_rn(0.0, ld_info_din(&P.info[v[k2]])));
+                    }
             }
-            const double tau = warp_min(q);   // arcte.py:359-360
-            for (int i0 = 0; i0 < S.nt; i0 += 64) {
-                int x[2];
-                double sx[2], dx[2];
+            const Threshold tau = make_threshold(warp_min(q));   // arcte.py:359-360
+            // sweep over the touched list: one 32-byte gather per node (in-degree included), nothing is reset
+            for (int i0 = 0; i0 < S.nt; i0 += 128) {
+                int x[4];
+                TableEntry o[4];
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
+                for (int k2 = 0; k2 < 4; ++k2) {
                     const int i = i0 + k2 * 32 + lane;
                     x[k2] = i < S.nt ? S.touched[i] : -1;
                 }
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2)
-                    if (x[k2] >= 0) {
-                        sx[k2] = ld_state(&S.sr[x[k2]]).x;
-                        dx[k2] = ld_info_din(&P.info[x[k2]]);
-                    }
+                for (int k2 = 0; k2 < 4; ++k2)
+                    if (x[k2] >= 0) o[k2] = ld_entry(S.T + x[k2]);
                 __syncwarp();
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
+                for (int k2 = 0; k2 < 4; ++k2) {
                     if (i0 + k2 * 32 >= S.nt) break;   // warp-uniform
                     bool in_sup = false, pass = false;
                     if (x[k2] >= 0) {
-                        st_state(&S.sr[x[k2]], make_double2(0.0, 0.0));
-                        in_sup = sx[k2] != 0.0;
-                        pass = in_sup && (__ddiv_rn(sx[k2], dx[k2]) >= tau);
+                        in_sup = o[k2].s != 0.0;
+                        pass = in_sup && quot_ge(o[k2].s, o[k2].d_in, tau);
                     }
                     support += __popc(__ballot_sync(kFull, in_sup));
                     const unsigned mp = __ballot_sync(kFull, pass);
@@ -801,6 +1036,8 @@ k_walk_batched(const PushParams P)
             }
         }
         __syncwarp();
+        PROF(7);
+        PROF_ADD(12, HASH ? (1 << S.lg) : S.nt);
         const bool emit = m > base_size;   // arcte.py:370
         bool write = false;
         if (emit) {
@@ -829,10 +1066,10 @@ k_walk_batched(const PushParams P)
         }
         __syncwarp();
         if (lane == 0 && (!emit || write)) {   // a seed whose members did not fit is re-run and counted then
-            wtot[WS_PUSHES] += ws[WS_PUSHES];
-            wtot[WS_EDGES] += ws[WS_EDGES];
-            wtot[WS_ENQ] += ws[WS_ENQ];
-            if (ws[WS_MAXQ] > wtot[WS_MAXQ]) wtot[WS_MAXQ] = ws[WS_MAXQ];
+            wtot[WS_PUSHES] += ws.pushes;
+            wtot[WS_EDGES] += ws.edges;
+            wtot[WS_ENQ] += ws.enq;
+            if (ws.maxq > wtot[WS_MAXQ]) wtot[WS_MAXQ] = ws.maxq;
             wtot[WS_SUPPORT] += support;
             wtot[WS_TOUCHED] += S.nt;
             wtot[WS_SEEDDEG] += si.len;
@@ -844,9 +1081,10 @@ k_walk_batched(const PushParams P)
         __syncwarp();
     }
 
-    if (HASH && lane == 0) {
-        P.tbl_clean[slot * 2 + 0] = S.clean[0];
-        P.tbl_clean[slot * 2 + 1] = S.clean[1];
+    PROF_FLUSH();
+    if (lane == 0) {
+        P.tbl_clean[slot * 2 + 0] = HASH ? S.clean[0] : S.epoch;
+        P.tbl_clean[slot * 2 + 1] = HASH ? S.clean[1] : 0;
     }
     if (lane == 0 && !P.debug_keep) {
         atomicAdd(&P.counters[PC_PUSHES], wtot[WS_PUSHES]);
@@ -877,9 +1115,16 @@ static int64_t pow2_ge(int64_t v)
 static int default_warps(const arcte_cuda_ctx *c)
 {
     int wps = c->warps_per_sm > 0 ? c->warps_per_sm : 16;
-    if (wps > 24) wps = 24;   // 7.8 KB of shared memory per warp
+    if (wps > 32) wps = 32;
     wps = ((wps + kWarpsPerCta - 1) / kWarpsPerCta) * kWarpsPerCta;
     return wps;
+}
+
+// Bytes of one slot: hash = two table halves of cap entries + a staging list of cap ints; direct-mapped =
+// one entry and one list cell per node.
+static double slot_bytes(int engine, int64_t cap, int64_t qcap)
+{
+    return (engine == ARCTE_ENGINE_BATCHED_HASH ? 68.0 : 36.0) * (double)cap + 4.0 * (double)qcap;
 }
 
 int batched_plan(arcte_cuda_ctx *c, int engine, int64_t n_work, int64_t *n_slots, int64_t *queue_cap)
@@ -892,33 +1137,36 @@ int batched_plan(arcte_cuda_ctx *c, int engine, int64_t n_work, int64_t *n_slots
     if (c->queue_cap_cfg <= 0 && qcap < 8192) qcap = 8192;
     if (qcap < 64) qcap = 64;
     qcap = pow2_ge(qcap);
-    size_t free_b = 0, total_b = 0;
-    ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
+    BatchedPool &bp = c->bpool;
+    int64_t cap;
     if (engine == ARCTE_ENGINE_BATCHED_HASH) {
-        BatchedPool &bp = c->bpool;
-        free_b += bp.tbl.bytes + bp.stage.bytes + bp.queue.bytes;
         // table region: two halves of cap entries; cap large enough for every node at 62.5 % load, bounded by memory
-        int64_t cap = c->tbl_cap_cfg > 0 ? pow2_ge(c->tbl_cap_cfg) : pow2_ge(2 * c->n);
+        cap = c->tbl_cap_cfg > 0 ? pow2_ge(c->tbl_cap_cfg) : pow2_ge(2 * c->n);
         if (cap < (1 << kInitLg)) cap = 1 << kInitLg;
         if (cap > ((int64_t)1 << 26)) cap = (int64_t)1 << 26;
-        const double budget = (double)free_b * pct / 100.0;
-        while (cap > (1 << kInitLg) && (double)want * (68.0 * (double)cap + 4.0 * (double)qcap) > budget) cap >>= 1;
-        if ((double)want * (68.0 * (double)cap + 4.0 * (double)qcap) > budget) {
-            want = (int64_t)(budget / (68.0 * (double)cap + 4.0 * (double)qcap));
-            want = (want / kWarpsPerCta) * kWarpsPerCta;
-            if (want < kWarpsPerCta) { set_error("not enough device memory for the walk tables"); return ARCTE_E_NOMEM; }
-        }
-        bp.plan_cap = cap;
     } else {
-        free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes;
-        const double budget = (double)free_b * pct / 100.0;
-        const double per_slot = 20.0 * (double)c->n + 4.0 * (double)qcap;
-        int64_t fit = (int64_t)(budget / per_slot);
-        fit = (fit / kWarpsPerCta) * kWarpsPerCta;
-        if (fit < kWarpsPerCta) { set_error("not enough device memory for the walk states of this graph"); return ARCTE_E_NOMEM; }
-        if (want > fit) want = fit;
+        cap = c->n;
     }
+    if (bp.mode == engine && bp.n_slots >= want && (engine == ARCTE_ENGINE_BATCHED_HASH ? bp.cap <= cap && bp.cap >= (1 << kInitLg) && c->tbl_cap_cfg == bp.cap_cfg
+                                                                                         : bp.cap == cap)) {
+        bp.plan_cap = bp.cap;   // keep the pool as it is
+        *n_slots = want;
+        *queue_cap = qcap;
+        return ARCTE_OK;
+    }
+    size_t free_b = 0, total_b = 0;
+    ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += bp.tbl.bytes + bp.stage.bytes + bp.queue.bytes;
+    const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
+    const double budget = (double)free_b * pct / 100.0;
+    if (engine == ARCTE_ENGINE_BATCHED_HASH)
+        while (cap > (1 << kInitLg) && (double)want * slot_bytes(engine, cap, qcap) > budget) cap >>= 1;
+    if ((double)want * slot_bytes(engine, cap, qcap) > budget) {
+        want = (int64_t)(budget / slot_bytes(engine, cap, qcap));
+        want = (want / kWarpsPerCta) * kWarpsPerCta;
+        if (want < kWarpsPerCta) { set_error("not enough device memory for the walk states of this graph"); return ARCTE_E_NOMEM; }
+    }
+    bp.plan_cap = cap;
     *n_slots = want;
     *queue_cap = qcap;
     return ARCTE_OK;
@@ -927,77 +1175,55 @@ int batched_plan(arcte_cuda_ctx *c, int engine, int64_t n_work, int64_t *n_slots
 int batched_ensure(arcte_cuda_ctx *c, int engine, int64_t n_slots, int64_t qcap)
 {
     if (!c->row_w_valid) { set_error("batched engine: graph not prepared"); return ARCTE_E_ARG; }
-    if (engine == ARCTE_ENGINE_BATCHED_HASH) {
-        BatchedPool &bp = c->bpool;
-        const int64_t cap = bp.plan_cap;
-        if (!(bp.n_slots >= n_slots && bp.cap == cap)) {
-            dev_free(bp.tbl);
-            dev_free(bp.stage);
-            dev_free(bp.clean);
-            bp.n_slots = 0;
-            ARCTE_TRY(dev_reserve(bp.tbl, sizeof(TableEntry) * 2 * (size_t)n_slots * (size_t)cap));
-            ARCTE_TRY(dev_reserve(bp.stage, sizeof(int32_t) * (size_t)n_slots * (size_t)cap));
-            ARCTE_TRY(dev_reserve(bp.clean, sizeof(int32_t) * 2 * (size_t)n_slots));
-            // nothing of the tables is initialised here: a warp makes the part it is about to use all-EMPTY
-            // the first time it needs it (tbl_clean), so an extraction never pays for the whole region
-            ARCTE_CUDA_TRY(cudaMemsetAsync(bp.clean.p, 0, sizeof(int32_t) * 2 * (size_t)n_slots, c->stream));
-            bp.n_slots = n_slots;
-            bp.cap = cap;
-        }
-        if (bp.queue_cap != qcap || bp.queue_slots < n_slots) {
-            dev_free(bp.queue);
-            ARCTE_TRY(dev_reserve(bp.queue, sizeof(int32_t) * (size_t)bp.n_slots * (size_t)qcap));
-            bp.queue_cap = qcap;
-            bp.queue_slots = bp.n_slots;
-        }
-        return ARCTE_OK;
+    BatchedPool &bp = c->bpool;
+    const int64_t cap = bp.plan_cap;
+    const bool hash = engine == ARCTE_ENGINE_BATCHED_HASH;
+    if (!(bp.mode == engine && bp.n_slots >= n_slots && bp.cap == cap)) {
+        dev_free(bp.tbl);
+        dev_free(bp.stage);
+        dev_free(bp.clean);
+        dev_free(bp.queue);
+        bp.n_slots = bp.queue_slots = 0;
+        bp.queue_cap = 0;
+        bp.mode = -1;
+        const size_t entries = (size_t)(hash ? 2 : 1) * (size_t)n_slots * (size_t)cap;
+        ARCTE_TRY(dev_reserve(bp.tbl, sizeof(TableEntry) * entries));
+        ARCTE_TRY(dev_reserve(bp.stage, sizeof(int32_t) * (size_t)n_slots * (size_t)cap));
+        ARCTE_TRY(dev_reserve(bp.clean, sizeof(int32_t) * 2 * (size_t)n_slots));
+        ARCTE_CUDA_TRY(cudaMemsetAsync(bp.clean.p, 0, sizeof(int32_t) * 2 * (size_t)n_slots, c->stream));
+        // hash: nothing of the tables is initialised here; a warp makes the part it is about to use all-EMPTY the
+        // first time it needs it (tbl_clean), so an extraction never pays for the whole region.
+        // direct-mapped: epoch 0 everywhere, once; walks tag their entries with epochs 1, 2, ...
+        if (!hash) ARCTE_CUDA_TRY(cudaMemsetAsync(bp.tbl.p, 0, sizeof(TableEntry) * entries, c->stream));
+        bp.n_slots = n_slots;
+        bp.cap = cap;
+        bp.cap_cfg = c->tbl_cap_cfg;
+        bp.mode = engine;
     }
-    SlotPool &sp = c->slots;
-    if (!(sp.n == c->n && sp.n_slots >= n_slots)) {
-        dev_free(sp.sr);
-        dev_free(sp.touched);
-        dev_free(sp.queue);
-        sp.n_slots = sp.queue_slots = 0;
-        sp.queue_cap = 0;
-        ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)n_slots * (size_t)c->n));
-        ARCTE_TRY(dev_reserve(sp.touched, sizeof(int32_t) * (size_t)n_slots * (size_t)c->n));
-        ARCTE_CUDA_TRY(cudaMemsetAsync(sp.sr.p, 0, sizeof(double2) * (size_t)n_slots * (size_t)c->n, c->stream));
-        sp.n = c->n;
-        sp.n_slots = n_slots;
-    }
-    if (sp.queue_cap != qcap || sp.queue_slots < n_slots) {
-        dev_free(sp.queue);
-        ARCTE_TRY(dev_reserve(sp.queue, sizeof(int32_t) * (size_t)sp.n_slots * (size_t)qcap));
-        sp.queue_cap = qcap;
-        sp.queue_slots = sp.n_slots;
+    if (bp.queue_cap != qcap || bp.queue_slots < n_slots) {
+        dev_free(bp.queue);
+        ARCTE_TRY(dev_reserve(bp.queue, sizeof(int32_t) * (size_t)bp.n_slots * (size_t)qcap));
+        bp.queue_cap = qcap;
+        bp.queue_slots = bp.n_slots;
     }
     return ARCTE_OK;
 }
 
 void batched_fill_params(arcte_cuda_ctx *c, int engine, PushParams &P)
 {
+    (void)engine;
+    const BatchedPool &bp = c->bpool;
     P.uniform_rows = c->uniform_rows ? 1 : 0;
     P.row_w = c->row_w.as<double>();
-    if (engine == ARCTE_ENGINE_BATCHED_HASH) {
-        const BatchedPool &bp = c->bpool;
-        P.tbl = bp.tbl.as<TableEntry>();
-        P.tbl_cap_max = bp.cap;
-        P.tbl_clean = bp.clean.as<int32_t>();
-        P.touched = bp.stage.as<int32_t>();
-        P.touched_stride = bp.cap;
-        P.queue = bp.queue.as<int32_t>();
-        P.queue_cap = bp.queue_cap;
-        P.sr = nullptr;
-    } else {
-        P.sr = c->slots.sr.as<double2>();
-        P.touched = c->slots.touched.as<int32_t>();
-        P.touched_stride = c->n;
-        P.queue = c->slots.queue.as<int32_t>();
-        P.queue_cap = c->slots.queue_cap;
-        P.tbl = nullptr;
-        P.tbl_cap_max = 0;
-        P.tbl_clean = nullptr;
-    }
+    P.edge_din = c->edge_din.as<double>();
+    P.tbl = bp.tbl.as<TableEntry>();
+    P.tbl_cap_max = bp.cap;
+    P.tbl_clean = bp.clean.as<int32_t>();
+    P.touched = bp.stage.as<int32_t>();
+    P.touched_stride = bp.cap;
+    P.queue = bp.queue.as<int32_t>();
+    P.queue_cap = bp.queue_cap;
+    P.sr = nullptr;
 }
 
 int batched_launch(arcte_cuda_ctx *c, int engine, const PushParams &P)

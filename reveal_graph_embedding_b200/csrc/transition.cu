@@ -121,6 +121,15 @@ k_edge_records(int64_t nnz, const int32_t *__restrict__ indices, const double *_
         wd[j] = make_double2(w[j], d_in[indices[j]]);
 }
 
+// In-degree of the target of every stored entry, read coalesced next to the column index by the batched
+// engine: no random gather of the node record per neighbour touch (similarity.py:194 / :214 need d_in[v]).
+__global__ void __launch_bounds__(256)
+k_edge_din(int64_t nnz, const int32_t *__restrict__ indices, const double *__restrict__ d_in, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += stride) out[j] = d_in[indices[j]];
+}
+
 // ---- K2a: seed keys -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_count_stats(int64_t n, const int32_t *__restrict__ colcnt, int64_t *__restrict__ out /*[2]: max, n_seeds*/)
@@ -263,6 +272,13 @@ int select_seeds(arcte_cuda_ctx *c)
         ++*launches;
     }
 #endif
+    ARCTE_TRY(dev_reserve(c->edge_din, sizeof(double) * (size_t)(c->nnz > 0 ? c->nnz : 1)));
+    if (c->nnz > 0) {
+        unsigned g = grid_for(c->nnz, 256);
+        if (g > (unsigned)c->sm_count * 16) g = (unsigned)c->sm_count * 16;
+        k_edge_din<<<g, 256, 0, st>>>(c->nnz, c->indices.as<int32_t>(), c->d_in.as<double>(), c->edge_din.as<double>());
+        ++*launches;
+    }
     const size_t m = (size_t)n + 1;
     ARCTE_TRY(dev_reserve(c->seeds, sizeof(int32_t) * (size_t)n));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(uint32_t) * m));

@@ -316,7 +316,7 @@ static int peak_snr_device(arcte_cuda_ctx *c, int64_t K, int64_t F, double *cm, 
 static int upload(arcte_cuda_ctx *c, DevBuf &b, const void *host, size_t bytes)
 {
     ARCTE_TRY(dev_reserve(b, bytes));
-    if (bytes > 0) ARCTE_CUDA_TRY(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (bytes > 0) ARCTE_TRY(copy_from_host(c, b.p, host, bytes));   // pageable scipy arrays at PCIe rate (hostcopy.cu)
     return ARCTE_OK;
 }
 
@@ -433,8 +433,7 @@ int arcte_cuda_normalize_columns(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_co
     ARCTE_TRY(upload(c, c->scratch[12], host_data_in, sizeof(double) * (size_t)nnz));
     ARCTE_TRY(normalize_columns_device(c, n_cols, nnz, c->scratch[11].as<int32_t>(), c->scratch[12].as<double>(),
                                        c->scratch[12].as<double>()));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_data_out, c->scratch[12].p, sizeof(double) * (size_t)nnz,
-                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_TRY(copy_to_host(c, host_data_out, c->scratch[12].p, sizeof(double) * (size_t)nnz));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;
 }
@@ -483,8 +482,7 @@ int arcte_cuda_chi2_contingency(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_col
     ARCTE_TRY(chi2_device(c, n_rows, n_cols, c->scratch[11].as<int64_t>(), c->scratch[12].as<int32_t>(), n_classes,
                           c->scratch[13].as<int64_t>(), c->scratch[14].as<int32_t>(), c->scratch[15].as<double>(),
                           c->scratch[7].as<double>()));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out, c->scratch[7].p, sizeof(double) * (size_t)n_classes * (size_t)n_cols,
-                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_TRY(copy_to_host(c, host_out, c->scratch[7].p, sizeof(double) * (size_t)n_classes * (size_t)n_cols));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;
 }
@@ -504,8 +502,7 @@ int arcte_cuda_peak_snr(arcte_cuda_ctx *c, int64_t n_classes, int64_t n_cols, do
     ARCTE_TRY(dev_reserve(c->scratch[6], sizeof(double) * (size_t)n_cols));
     ARCTE_TRY(peak_snr_device(c, n_classes, n_cols, c->scratch[7].as<double>(), c->scratch[6].as<double>()));
     ARCTE_CUDA_TRY(cudaMemcpyAsync(host_cm_inout, c->scratch[7].p, bytes, cudaMemcpyDeviceToHost, c->stream));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_weights_out, c->scratch[6].p, sizeof(double) * (size_t)n_cols,
-                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_TRY(copy_to_host(c, host_weights_out, c->scratch[6].p, sizeof(double) * (size_t)n_cols));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;
 }
@@ -526,8 +523,7 @@ int arcte_cuda_chi2_psnr_weights(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_co
                           c->scratch[13].as<int64_t>(), c->scratch[14].as<int32_t>(), c->scratch[15].as<double>(),
                           c->scratch[7].as<double>()));
     ARCTE_TRY(peak_snr_device(c, n_classes, n_cols, c->scratch[7].as<double>(), c->scratch[6].as<double>()));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_weights_out, c->scratch[6].p, sizeof(double) * (size_t)n_cols,
-                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_TRY(copy_to_host(c, host_weights_out, c->scratch[6].p, sizeof(double) * (size_t)n_cols));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;
 }
@@ -563,13 +559,10 @@ int arcte_cuda_community_weighting(arcte_cuda_ctx *c, int64_t n_rows, int64_t n_
     ARCTE_TRY(community_weighting_device(c, n_rows, n_cols, nnz, c->scratch[11].as<int64_t>(),
                                          c->scratch[12].as<int32_t>(), c->scratch[13].as<double>(),
                                          c->scratch[14].as<double>(), c->scratch[15], c->scratch[6], c->scratch[7], &kept));
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_indptr, c->scratch[15].p, sizeof(int64_t) * (size_t)(n_rows + 1),
-                                   cudaMemcpyDeviceToHost, st));
+    ARCTE_TRY(copy_to_host(c, host_out_indptr, c->scratch[15].p, sizeof(int64_t) * (size_t)(n_rows + 1)));
     if (kept > 0) {
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_indices, c->scratch[6].p, sizeof(int32_t) * (size_t)kept,
-                                       cudaMemcpyDeviceToHost, st));
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_out_data, c->scratch[7].p, sizeof(double) * (size_t)kept,
-                                       cudaMemcpyDeviceToHost, st));
+        ARCTE_TRY(copy_to_host(c, host_out_indices, c->scratch[6].p, sizeof(int32_t) * (size_t)kept));
+        ARCTE_TRY(copy_to_host(c, host_out_data, c->scratch[7].p, sizeof(double) * (size_t)kept));
     }
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     *out_nnz = kept;
@@ -686,14 +679,11 @@ int arcte_cuda_get_fold(arcte_cuda_ctx *c, int which, int64_t *host_indptr, int3
     CHECK_CTX(c);
     if (!c->fo_valid || which < 0 || which > 1 || !host_indptr) { set_error("get_fold: call weighted_fold first"); return ARCTE_E_ARG; }
     const int64_t rows = c->fo_rows[which], nnz = c->fo_nnz[which];
-    ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indptr, c->fo_indptr[which].p, sizeof(int64_t) * (size_t)(rows + 1),
-                                   cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_TRY(copy_to_host(c, host_indptr, c->fo_indptr[which].p, sizeof(int64_t) * (size_t)(rows + 1)));
     if (nnz > 0) {
         if (!host_indices || !host_data) { set_error("get_fold: null output"); return ARCTE_E_ARG; }
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_indices, c->fo_indices[which].p, sizeof(int32_t) * (size_t)nnz,
-                                       cudaMemcpyDeviceToHost, c->stream));
-        ARCTE_CUDA_TRY(cudaMemcpyAsync(host_data, c->fo_data[which].p, sizeof(double) * (size_t)nnz,
-                                       cudaMemcpyDeviceToHost, c->stream));
+        ARCTE_TRY(copy_to_host(c, host_indices, c->fo_indices[which].p, sizeof(int32_t) * (size_t)nnz));
+        ARCTE_TRY(copy_to_host(c, host_data, c->fo_data[which].p, sizeof(double) * (size_t)nnz));
     }
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ARCTE_OK;

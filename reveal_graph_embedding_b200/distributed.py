@@ -1,14 +1,23 @@
 """Seed sharding across GPUs, one process per GPU (torchrun / torch.distributed).
 
-The reference fans seeds out to a multiprocessing pool and sums the workers' matrices
-on the parent (arcte.py:650-673).  Here every rank holds the whole graph, walks the
-seeds at positions rank, rank + world, ... of the degree-sorted seed list
-(roundrobin_chunks, arcte.py:19-23) and the per-rank member segments are joined by ONE
-exchange step: an NCCL all-gather of (seed, count, offset, members).  torch is used for
-the process group and the collective only; the arrays it moves are filled and consumed
-by libarcte_cuda through raw device pointers.
+The reference fans seeds out to a multiprocessing pool and sums the workers' matrices on the parent
+(arcte.py:650-673).  Here every rank holds the whole graph, walks the seeds at positions rank,
+rank + world, ... of the degree-sorted seed list (roundrobin_chunks, arcte.py:19-23) and owns a contiguous
+block of rows of the result.  The ONE exchange step runs inside libarcte_cuda (csrc/exchange.cu): every
+community is split by destination row block on the device and the pieces cross NVLink once, in a single
+grouped NCCL send/recv; each rank then assembles its own rows.  torch.distributed is used for the
+plumbing only: the process group tells the ranks apart, carries the 128-byte NCCL id once and a handful of
+integers per call.
+
+The rows come home through every rank's own PCIe link: rank 0 creates the result arrays in shared memory
+(/dev/shm), every rank streams its row block into its slice (csrc/hostcopy.cu), and rank 0 returns the
+matrix (the other ranks return None; ARCTE_CUDA_RESULT_ON_ALL_RANKS=1 maps it on every rank).
 """
+import os
 import sys
+import uuid
+
+import numpy as np
 
 
 def _dist():
@@ -31,200 +40,159 @@ def shard_positions(n_seeds, rank, world):
     return range(rank, n_seeds, world)
 
 
-def allgather_segments(seg_seed, seg_count, seg_offset, members, group=None):
-    """All-gather four 1-D tensors of rank-dependent length.
-
-    seg_seed/seg_count: int32 [S_r]; seg_offset: int64 [S_r]; members: int32 [M_r].
-    Returns a list over ranks of (seg_seed, seg_count, seg_offset, members) tensor views
-    (on the same device as the inputs).  Sizes are exchanged first, then every array is
-    padded to the largest rank's size so a single fixed-size all-gather per array moves it.
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    dev = seg_seed.device
-    sizes = torch.tensor([seg_seed.numel(), members.numel()], dtype=torch.int64, device=dev)
-    all_sizes = torch.empty(world * 2, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-    all_sizes = all_sizes.view(world, 2).cpu()
-    s_max = max(int(all_sizes[:, 0].max()), 1)
-    m_max = max(int(all_sizes[:, 1].max()), 1)
-
-    def gather(x, width, dtype):
-        send = torch.zeros(width, dtype=dtype, device=dev)
-        send[:x.numel()] = x
-        recv = torch.empty(world * width, dtype=dtype, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        return recv.view(world, width)
-
-    g_seed = gather(seg_seed, s_max, torch.int32)
-    g_count = gather(seg_count, s_max, torch.int32)
-    g_off = gather(seg_offset, s_max, torch.int64)
-    g_mem = gather(members, m_max, torch.int32)
-    parts = []
-    for r in range(world):
-        S, M = int(all_sizes[r, 0]), int(all_sizes[r, 1])
-        parts.append((g_seed[r, :S], g_count[r, :S], g_off[r, :S], g_mem[r, :M]))
-    return parts
-
-
-def result_on_all_ranks():
-    """ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: every rank assembles and returns the matrix.
-    Default: rank 0 only (the others return None) -- copying a multi-gigabyte matrix to
-    the host once per rank would dominate the call."""
-    import os
-    return os.environ.get("ARCTE_CUDA_RESULT_ON_ALL_RANKS", "0") == "1"
-
-
-class _DeviceArray:
-    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
-
-    def __init__(self, address, count, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
-                                         "data": (int(address), False), "version": 2}
-
-
-def _view(address, count, typestr, device):
-    import torch
-    if count == 0:
-        dt = {"<i8": torch.int64, "<i4": torch.int32, "<f8": torch.float64}[typestr]
-        return torch.empty(0, dtype=dt, device=device)
-    return torch.as_tensor(_DeviceArray(address, count, typestr), device=device)
-
-
 def row_range(n, rank, world):
     """Rows of the feature matrix rank `rank` assembles: equal contiguous blocks."""
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
-def extract_and_concatenate(eng, rule, rho_eff, epsilon):
-    """Steps 1-3 of the distributed call, everything staying in HBM.
+def result_on_all_ranks():
+    """ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: every rank returns the matrix (all of them map the same shared
+    memory).  Default: rank 0 only, the others return None."""
+    return os.environ.get("ARCTE_CUDA_RESULT_ON_ALL_RANKS", "0") == "1"
 
-    1. walk this rank's round-robin shard of the seeds (K2b-K4);
-    2. ONE exchange of the walk results: NCCL all-gather of the member segments;
-    3. every rank assembles the row block [n*r/G, n*(r+1)/G) of the feature matrix (K5 on 1/G
-       of the entries); the blocks are concatenated on rank 0 with NCCL send/recv.
-    Returns (indptr, indices, data, nnz) device tensors on rank 0, None on the other ranks.
-    """
-    import numpy as np
+
+# ------------------------------------------------------------------------------------------------
+# host-side collectives: a few integers / bytes per call, over whatever backend the group has
+# ------------------------------------------------------------------------------------------------
+def _device_for_group(dist):
     import torch
-    import torch.distributed as dist
+    backend = dist.get_backend()
+    if "nccl" in str(backend):
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def all_gather_int64(values):
+    """values: sequence of ints, the same length on every rank -> int64 array [world, len]."""
+    import torch
+    dist = _dist()
+    dev = _device_for_group(dist)
+    mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    out = torch.empty(dist.get_world_size() * mine.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape(dist.get_world_size(), -1)
+
+
+def broadcast_bytes(payload, n_bytes, src=0):
+    """`payload` (bytes of length n_bytes on rank src, ignored elsewhere) -> the same bytes on every rank."""
+    import torch
+    dist = _dist()
+    dev = _device_for_group(dist)
+    if dist.get_rank() == src:
+        t = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    else:
+        t = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tolist())
+
+
+# ------------------------------------------------------------------------------------------------
+# the result in shared memory: one file per array under /dev/shm, mapped by every rank
+# ------------------------------------------------------------------------------------------------
+SHM_DIR = os.environ.get("ARCTE_CUDA_SHM_DIR", "/dev/shm")
+
+
+def block_offsets(block_nnz):
+    """Exclusive prefix of the per-rank stored-entry counts (+ total)."""
+    return np.concatenate([[0], np.cumsum(np.asarray(block_nnz, dtype=np.int64))])
+
+
+class SharedResult:
+    """indptr int64[n+1], indices int32[total], data float64[total] backed by files in SHM_DIR.
+    Rank 0 creates them, everybody maps them; the files are unlinked as soon as every rank has them open
+    (the memory lives as long as a mapping does)."""
+
+    def __init__(self, tag, n, total, create):
+        self.paths = [os.path.join(SHM_DIR, "arcte_%s_%s" % (tag, k)) for k in ("indptr", "indices", "data")]
+        shapes = [((n + 1,), np.int64), ((max(total, 1),), np.int32), ((max(total, 1),), np.float64)]
+        mode = "w+" if create else "r+"
+        self.arrays = [np.memmap(p, dtype=dt, mode=mode, shape=sh) for p, (sh, dt) in zip(self.paths, shapes)]
+        self.n, self.total = n, total
+
+    def unlink(self):
+        for p in self.paths:
+            try:
+                os.unlink(p)
+            except FileNotFoundError:
+                pass
+
+    def csr(self):
+        import scipy.sparse as sparse
+        indptr, indices, data = (np.asarray(a) for a in self.arrays)
+        indices, data = indices[:self.total], data[:self.total]
+        if max(2 * self.n, self.total) < 2 ** 31:
+            indptr = indptr.astype(np.int32)
+        else:
+            indices = indices.astype(np.int64)
+        return sparse.csr_matrix((data, indices, indptr), shape=(self.n, 2 * self.n), copy=False)
+
+
+def place_block(result, rank, world, offsets, blk_indptr):
+    """Row pointers of one rank's block into the shared indptr: neighbouring blocks write the same value
+    at the row they share."""
+    lo, hi = row_range(result.n, rank, world)
+    result.arrays[0][lo:hi + 1] = blk_indptr + offsets[rank]
+    return lo, hi
+
+
+# ------------------------------------------------------------------------------------------------
+def ensure_communicator(eng):
+    """NCCL communicator of this engine's context over all ranks of the default process group (created on
+    first use; the id comes from rank 0's library and travels through the process group)."""
+    dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
-    dev = torch.device("cuda", eng.device)
-    eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
-    parts, keep = gather_engine_segments(eng)
-    n = eng.n
-    lo, hi = row_range(n, rank, world)
-    eng.assemble(parts, row_lo=lo, row_hi=hi)
-    del keep
-    p_indptr, p_indices, p_data, n_rows, nnz = eng.features_device()
-    sizes = torch.tensor([nnz], dtype=torch.int64, device=dev)
-    all_nnz = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_nnz, sizes)
-    all_nnz = all_nnz.cpu().numpy()
-    offsets = np.concatenate([[0], np.cumsum(all_nnz)])
-    total = int(offsets[-1])
-    blk_indptr = _view(p_indptr, n_rows + 1, "<i8", dev)
-    blk_indices = _view(p_indices, nnz, "<i4", dev)
-    blk_data = _view(p_data, nnz, "<f8", dev)
-    torch.cuda.synchronize(dev)
-    if rank != 0:
-        ops = [dist.P2POp(dist.isend, blk_indptr, 0)]
-        if nnz > 0:
-            ops += [dist.P2POp(dist.isend, blk_indices, 0), dist.P2POp(dist.isend, blk_data, 0)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        torch.cuda.synchronize(dev)
-        return None
-    indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    indices = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    data = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
-    tmp_ptr = []
-    ops = []
-    for r in range(1, world):
-        rlo, rhi = row_range(n, r, world)
-        t = torch.empty(rhi - rlo + 1, dtype=torch.int64, device=dev)
-        tmp_ptr.append((r, rlo, rhi, t))
-        ops.append(dist.P2POp(dist.irecv, t, r))
-        if all_nnz[r] > 0:
-            ops.append(dist.P2POp(dist.irecv, indices[int(offsets[r]):int(offsets[r + 1])], r))
-            ops.append(dist.P2POp(dist.irecv, data[int(offsets[r]):int(offsets[r + 1])], r))
-    reqs = dist.batch_isend_irecv(ops) if ops else []
-    indptr[lo:hi + 1] = blk_indptr
-    indices[:nnz] = blk_indices
-    data[:nnz] = blk_data
-    for r in reqs:
-        r.wait()
-    for r, rlo, rhi, t in tmp_ptr:
-        indptr[rlo:rhi + 1] = t + int(offsets[r])
-    torch.cuda.synchronize(dev)
-    return indptr, indices, data, total
+    if eng.comm_info()[:2] == (world, rank):
+        return
+    uid = eng.comm_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 128, src=0)
+    eng.comm_init(world, rank, uid)
 
 
 def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_ranks=None):
-    """One rank's share of arcte() inside a torch.distributed job: see extract_and_concatenate.
-    Rank 0 copies the matrix to the host and returns it; the other ranks return None.  With
-    all_ranks (ARCTE_CUDA_RESULT_ON_ALL_RANKS=1) every rank assembles and returns the matrix."""
-    import numpy as np
-    import scipy.sparse as sparse
-    import torch
-    import torch.distributed as dist
-    from . import hostmem
+    """One rank's share of arcte() inside a torch.distributed job.  Rank 0 returns the matrix, the other
+    ranks None (all_ranks / ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: everybody)."""
     from .engine import get_engine
+    dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
-    eng = engine or get_engine(torch.cuda.current_device())
+    if world > 16:
+        raise RuntimeError("arcte: at most 16 ranks (one box); got %d" % world)
+    if engine is None:
+        local = os.environ.get("LOCAL_RANK")
+        if local is None:
+            import torch
+            local = torch.cuda.current_device()
+        engine = get_engine(int(local))
+    eng = engine
     if upload:
         eng.set_graph(A, canonical=True)
     if all_ranks is None:
         all_ranks = result_on_all_ranks()
-    if all_ranks:
-        eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
-        parts, keep = gather_engine_segments(eng)
-        eng.assemble(parts)
-        del keep
-        return eng.features()
-    out = extract_and_concatenate(eng, rule, rho_eff, epsilon)
-    if out is None:
-        return None
-    indptr, indices, data, total = out
+    ensure_communicator(eng)
     n = eng.n
-    # device -> host into pooled page-locked buffers
-    h_indices = hostmem.empty(max(total, 1), np.int32)
-    torch.from_numpy(h_indices).copy_(indices)
-    h_indptr = indptr.cpu().numpy()
-    # values: ones pre-filled on the host + self-loop diagonals patched, else a device-to-host copy
-    h_data = hostmem.ones(max(total, 1))
-    if h_data is not None:
-        rows, rank_in_row = eng.self_loop_rows()
-        if rows.size:
-            h_data[h_indptr[rows].astype(np.int64) + rank_in_row] = 2.0
-    else:
-        h_data = hostmem.empty(max(total, 1), np.float64)
-        torch.from_numpy(h_data).copy_(data)
-    hostmem.start_pending()
-    h_indices, h_data = h_indices[:total], h_data[:total]
-    if max(2 * n, total) < 2 ** 31:
-        h_indptr = h_indptr.astype(np.int32)
-    else:
-        h_indices = h_indices.astype(np.int64)
-    return sparse.csr_matrix((h_data, h_indices, h_indptr), shape=(n, 2 * n), copy=False)
-
-
-def gather_engine_segments(eng):
-    """Copy the engine's device-resident segments into torch tensors, all-gather them over
-    NCCL and return them as raw-pointer parts for Engine.assemble (plus the tensors that
-    must stay alive until assemble returns)."""
-    import torch
-    dev = torch.device("cuda", eng.device)
-    S, M = eng.n_segments, eng.n_members
-    seg_seed = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
-    seg_count = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
-    seg_offset = torch.empty(max(S, 1), dtype=torch.int64, device=dev)
-    members = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    torch.cuda.synchronize(dev)
-    eng.export_segments(seg_seed.data_ptr(), seg_count.data_ptr(), seg_offset.data_ptr(), members.data_ptr())
-    gathered = allgather_segments(seg_seed[:S], seg_count[:S], seg_offset[:S], members[:M])
-    torch.cuda.synchronize(dev)
-    parts = [(int(a.numel()), int(d.numel()), a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr())
-             for (a, b, c, d) in gathered]
-    return parts, gathered
+    eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
+    nnz = eng.exchange_assemble()
+    # sizes of all blocks + a name for the shared arrays (rank 0 picks it)
+    tag_bits = uuid.uuid4().int & ((1 << 62) - 1) if rank == 0 else 0
+    table = all_gather_int64([nnz, tag_bits])
+    offsets = block_offsets(table[:, 0])
+    total = int(offsets[-1])
+    tag = "%016x_%d" % (int(table[0, 1]), os.getuid())
+    res = None
+    if rank == 0:
+        res = SharedResult(tag, n, total, create=True)
+    dist.barrier()
+    if rank != 0:
+        res = SharedResult(tag, n, total, create=False)
+    o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
+    lo, hi = row_range(n, rank, world)
+    ip = np.empty(hi - lo + 1, dtype=np.int64)
+    indices, data = np.asarray(res.arrays[1]), np.asarray(res.arrays[2])
+    structural = eng._values_structural
+    eng.fetch_block(ip, indices[o0:o1], data[o0:o1], values_are_ones=structural)
+    if structural:
+        eng.patch_self_loops(data[o0:o1], ip, lo, hi)
+    place_block(res, rank, world, offsets, ip)
+    dist.barrier()          # every block is in place (the mappings share pages: nothing to flush)
+    if rank == 0:
+        res.unlink()
+    return res.csr() if (rank == 0 or all_ranks) else None

@@ -24,12 +24,14 @@ Differences from the reference, all on purpose:
   * number_of_threads larger than the number of seeds works (the reference crashes on an
     empty chunk, arcte.py:19-23).
 """
+import os
 import threading
+import time
 
 import numpy as np
 import scipy.sparse as sparse
 
-from ... import distributed, hostmem
+from ... import distributed
 from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, canonical_csr, device_count,
                        get_engine)
 
@@ -82,8 +84,6 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
         e.set_graph(A, canonical=True)
         e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
 
-    import os
-    import time
     dbg = os.environ.get("ARCTE_CUDA_DEBUG")
     t0 = time.perf_counter()
     run_parallel(walk)
@@ -102,40 +102,28 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     nnz = np.array([e.out_nnz for e in engines], dtype=np.int64)
     offsets = np.concatenate([[0], np.cumsum(nnz)])
     total = int(offsets[-1])
-    indices = hostmem.empty(max(total, 1), np.int32)
-    # every stored value is 1.0 except self-loop diagonals: a pre-filled block of ones saves the
-    # device-to-host copy of two thirds of the bytes (Engine.structural_values)
-    data = hostmem.ones(max(total, 1))
-    prefilled = data is not None
-    if not prefilled:
-        data = hostmem.empty(max(total, 1), np.float64)
+    # plain numpy result arrays; every GPU streams its row block into its slice over its own PCIe link
+    # (csrc/hostcopy.cu).  Every stored value is 1.0 except self-loop diagonals (arcte.py:379-381, :676-679):
+    # the values are written by the copy threads, not copied.
+    indices = np.empty(total, dtype=np.int32)
+    data = np.empty(total, dtype=np.float64)
     indptr = np.empty(n + 1, dtype=np.int64)
-    blocks = [None] * n_gpus
+    threads_each = max(2, (os.cpu_count() or 8) // n_gpus)
 
     def fetch(rank):
         lo, hi = distributed.row_range(n, rank, n_gpus)
         ip = np.empty(hi - lo + 1, dtype=np.int64)
         o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
-        engines[rank].features_into(ip, indices[o0:o1], None if prefilled else data[o0:o1])
-        blocks[rank] = (lo, hi, ip)
+        engines[rank].fetch_block(ip, indices[o0:o1], data[o0:o1], values_are_ones=True, n_threads=threads_each)
+        engines[rank].patch_self_loops(data[o0:o1], ip, lo, hi)
+        indptr[lo:hi + 1] = ip + offsets[rank]   # neighbouring blocks write the same value at their common row
 
     run_parallel(fetch)
-    if prefilled:
-        rows, rank_in_row = engines[0].self_loop_rows()
-        if rows.size:
-            full_ptr = np.empty(n + 1, dtype=np.int64)
-            for r, (lo, hi, ip) in enumerate(blocks):
-                full_ptr[lo:hi + 1] = ip + offsets[r]
-            data[full_ptr[rows] + rank_in_row] = 2.0
     t3 = time.perf_counter()
     if dbg:
         import sys
         print("[arcte] in-process %d GPUs: upload+walk %.1f ms, exchange+assemble %.1f ms, fetch %.1f ms"
               % (n_gpus, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr)
-    hostmem.start_pending()
-    for rank, (lo, hi, ip) in enumerate(blocks):
-        indptr[lo:hi + 1] = ip + offsets[rank]
-    indices, data = indices[:total], data[:total]
     if max(2 * n, total) < 2 ** 31:
         indptr = indptr.astype(np.int32)
     else:

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import scipy.sparse as sparse
 
-from . import _lib, hostmem
+from . import _lib
 from ._lib import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, SCHEDULE_FIFO, SCHEDULE_FRONTIER,  # noqa: F401
                    ArcteCudaError, check, ptr)
 
@@ -266,21 +266,31 @@ class Engine:
         check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices) if self.out_nnz else None,
                                               ptr(data) if (self.out_nnz and data is not None) else None))
 
+    def fetch_block(self, indptr, indices, data, values_are_ones=False, n_threads=0):
+        """Copy the assembled block into caller-owned plain numpy arrays (slices of larger arrays are fine):
+        indptr int64[rows+1], indices int32[nnz], data float64[nnz] (each may be None).  With values_are_ones
+        the values are not copied but written as 1.0 by the copy threads (the caller patches the 2.0s)."""
+        rows = getattr(self, "out_rows", self.n)
+        assert indptr is None or (indptr.dtype == np.int64 and indptr.size == rows + 1 and indptr.flags.c_contiguous)
+        assert indices is None or (indices.dtype == np.int32 and indices.size == self.out_nnz and indices.flags.c_contiguous)
+        assert data is None or (data.dtype == np.float64 and data.size == self.out_nnz and data.flags.c_contiguous)
+        check(self._L.arcte_cuda_fetch_features(self._h, ptr(indptr), ptr(indices) if self.out_nnz else None,
+                                                ptr(data) if self.out_nnz else None, int(bool(values_are_ones)),
+                                                int(n_threads)))
+
     def features(self):
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
         nnz = self.out_nnz
         if getattr(self, "out_rows", self.n) != self.n:
             raise ArcteCudaError("features(): only a row block is assembled; use the distributed path")
         indptr = np.empty(self.n + 1, dtype=np.int64)
-        indices = hostmem.empty(max(nnz, 1), np.int32)   # page-locked for large results
-        check(self._L.arcte_cuda_get_features(self._h, ptr(indptr), ptr(indices), None))
-        data = self.structural_values(indptr)            # ones pre-filled on the host: no copy of the values
-        if data is None:
-            data = hostmem.empty(max(nnz, 1), np.float64)
-            check(self._L.arcte_cuda_get_features(self._h, None, None, ptr(data)))
-        hostmem.start_pending()
-        indices = indices[:nnz]
-        data = data[:nnz]
+        indices = np.empty(nnz, dtype=np.int32)
+        data = np.empty(nnz, dtype=np.float64)
+        # every stored value is 1.0 (arcte.py:379-381, :676-679) except the identity entry of a self-loop row:
+        # unless the values were changed on the device they are written on the host, not copied
+        self.fetch_block(indptr, indices, data, values_are_ones=self._values_structural)
+        if self._values_structural:
+            self.patch_self_loops(data, indptr)
         if max(2 * self.n, nnz) < 2 ** 31:
             indptr = indptr.astype(np.int32)
         else:
@@ -303,12 +313,11 @@ class Engine:
     def normalize_columns(self, features):
         """embedding/common.py:49-67 on any scipy sparse matrix; returns a new CSR."""
         shape, indptr, indices, data = self._csr_arrays(features)
-        out = hostmem.empty(data.size, np.float64)   # page-locked for large results
+        out = np.empty(data.size, np.float64)   # page-locked for large results
         check(self._L.arcte_cuda_normalize_columns(self._h, shape[0], shape[1], ptr(indptr),
                                                    ptr(indices) if data.size else None,
                                                    ptr(data) if data.size else None,
                                                    ptr(out) if data.size else None))
-        hostmem.start_pending()
         idx_t = np.int32 if max(shape[1], data.size) < 2 ** 31 else np.int64
         return sparse.csr_matrix((out, indices.astype(idx_t, copy=False), indptr.astype(idx_t)), shape=shape)
 
@@ -327,25 +336,15 @@ class Engine:
             self._loops = (rows[k], k - ip[rows[k]])
         return self._loops
 
-    def structural_values(self, out_indptr, row_lo=0, row_hi=None):
-        """The value array of the assembled block rows [row_lo, row_hi) WITHOUT copying it from the
-        device: every stored value is 1.0 (arcte.py:379-381, :676-679) except the identity entry of
-        a row with a self loop, which is 2.0.  Returns a page-locked array of ones with those entries
-        patched, or None when no pre-filled block is ready / the values were changed on the device
-        (normalize_features); the caller then copies the values as usual.  out_indptr: the block's
-        row pointers (starting at 0)."""
-        if not self._values_structural:
-            return None
-        nnz = int(out_indptr[-1])
-        data = hostmem.ones(max(nnz, 1))
-        if data is None:
-            return None
+    def patch_self_loops(self, data, out_indptr, row_lo=0, row_hi=None):
+        """Sets the identity entries of self-loop rows to 2.0 in a value array of ones (arcte.py:676-679:
+        I + pattern(A) has 2.0 where A stores its diagonal).  out_indptr: row pointers of the block
+        [row_lo, row_hi), starting at 0; the diagonal is the rank-th base-block column of its row."""
         row_hi = self.n if row_hi is None else row_hi
         rows, rank = self.self_loop_rows()
         m = (rows >= row_lo) & (rows < row_hi)
-        if m.any():   # the diagonal is the rank-th base-block column of its row (columns < n come first)
+        if m.any():
             data[np.asarray(out_indptr)[rows[m] - row_lo].astype(np.int64) + rank[m]] = 2.0
-        return data
 
     def chi2_contingency(self, X_train, Y):
         """embedding/community_weighting.py:11-45; Y = binarised label matrix (sparse)."""
@@ -389,14 +388,13 @@ class Engine:
         if w.size != shape[1]:
             raise ValueError("one community weight per column is required")
         out_indptr = np.zeros(shape[0] + 1, dtype=np.int64)
-        out_indices = hostmem.empty(max(data.size, 1), np.int32)
-        out_data = hostmem.empty(max(data.size, 1), np.float64)
+        out_indices = np.empty(max(data.size, 1), np.int32)
+        out_data = np.empty(max(data.size, 1), np.float64)
         nnz = C.c_int64()
         check(self._L.arcte_cuda_community_weighting(self._h, shape[0], shape[1], ptr(indptr),
                                                      ptr(indices) if data.size else None,
                                                      ptr(data) if data.size else None, ptr(w) if w.size else None,
                                                      ptr(out_indptr), ptr(out_indices), ptr(out_data), C.byref(nnz)))
-        hostmem.start_pending()
         k = nnz.value
         idx_t = np.int32 if max(shape[1], k) < 2 ** 31 else np.int64
         return sparse.csr_matrix((out_data[:k], out_indices[:k].astype(idx_t, copy=False), out_indptr.astype(idx_t)),
@@ -432,13 +430,12 @@ class Engine:
         out = []
         for which, rows, nnz in ((0, train.size, a.value), (1, test.size, b.value)):
             indptr = np.zeros(rows + 1, dtype=np.int64)
-            indices = hostmem.empty(max(nnz, 1), np.int32)
-            data = hostmem.empty(max(nnz, 1), np.float64)
+            indices = np.empty(max(nnz, 1), np.int32)
+            data = np.empty(max(nnz, 1), np.float64)
             check(self._L.arcte_cuda_get_fold(self._h, which, ptr(indptr), ptr(indices), ptr(data)))
             idx_t = np.int32 if max(self.stored_shape[1], nnz) < 2 ** 31 else np.int64
             out.append(sparse.csr_matrix((data[:nnz], indices[:nnz].astype(idx_t, copy=False), indptr.astype(idx_t)),
                                          shape=(rows, self.stored_shape[1])))
-        hostmem.start_pending()
         return out[0], out[1]
 
     def timer_start(self):
