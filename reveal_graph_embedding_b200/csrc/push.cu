@@ -48,7 +48,7 @@ template <int RULE>
 __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restrict__ sr,
                                           int32_t *__restrict__ touched, int32_t *__restrict__ queue,
                                           Walk &wk, unsigned long long *ws, int u, double2 su, unsigned begin,
-                                          unsigned len, double eps, bool scan, int lane, unsigned lt)
+                                          unsigned len, const Threshold &eps, bool scan, int lane, unsigned lt)
 {
     double c;
     if (RULE == ARCTE_RULE_ABSORBING) {
@@ -76,8 +76,13 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
 #else
     const double *__restrict__ wgt = P.w + begin;
 #endif
+    // every row of an unweighted graph holds one repeated transition weight (transition.cu: k_row_uniform):
+    // one product per push instead of one weight load per stored entry
+    const bool uni = P.uniform_rows != 0;
+    const double p_uni = uni ? __dmul_rn(c, P.row_w[u]) : 0.0;
+    const double *__restrict__ edin = P.edge_din + begin;   // in-degree of every entry's target, coalesced
     for (unsigned base = 0; base < len; base += 32 * kPushUnroll) {
-        // phase 1: neighbour ids and transition weights of up to kPushUnroll chunks
+        // phase 1: neighbour ids, transition weights and target in-degrees of up to kPushUnroll chunks
         int v[kPushUnroll];
         double p[kPushUnroll];
         double dv[kPushUnroll];
@@ -92,7 +97,8 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
                 p[k] = __dmul_rn(c, e.x);
                 dv[k] = e.y;
 #else
-                p[k] = __dmul_rn(c, ld_weight(wgt + j));
+                p[k] = uni ? p_uni : __dmul_rn(c, ld_weight(wgt + j));
+                dv[k] = edin[j];
 #endif
             }
         }
@@ -102,9 +108,6 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
         for (int k = 0; k < kPushUnroll; ++k) {
             if (v[k] >= 0) {
                 o[k] = ld_state(&sr[v[k]]);
-#if !ARCTE_EDGE_RECORDS
-                dv[k] = ld_info_din(&P.info[v[k]]);
-#endif
             }
         }
         // phase 3: update and store (neighbours of one node are distinct: no ordering needed)
@@ -122,7 +125,7 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
                 }
                 st_state(&sr[v[k]], nw);
                 if ((o[k].x == 0.0 && o[k].y == 0.0) && (nw.x != 0.0 || nw.y != 0.0)) f_new |= 1u << k;
-                if (scan && __ddiv_rn(nw.y, dv[k]) >= eps) f_enq |= 1u << k;  // similarity.py:194 / :214
+                if (scan && quot_ge(nw.y, dv[k], eps)) f_enq |= 1u << k;  // similarity.py:194 / :214
             }
         }
         // phase 4: ordered appends (CSR order = chunk order, then lane order).  Every node
@@ -198,7 +201,7 @@ k_push_threshold(const PushParams P)
         if ((int64_t)k >= P.n_work) break;
         const int pos = P.work_ids ? P.work_ids[k] : (int)k;
         const int seed = P.work_seed[pos];
-        const double eps = P.work_eps[pos];
+        const Threshold eps = make_threshold(P.work_eps[pos]);
 
         Walk wk;
         wk.head = wk.tail = 0;
@@ -222,14 +225,14 @@ k_push_threshold(const PushParams P)
         NodeInfo iu = ld_info(&P.info[seed]);
         bool first = true, ok = true;
         for (;;) {
-            if (first || __ddiv_rn(su.y, iu.d_in) >= eps) {  // similarity.py:204
+            if (first || quot_ge(su.y, iu.d_in, eps)) {  // similarity.py:204
                 ok = push_node<RULE>(P, sr, touched, queue, wk, ws, u, su, iu.begin, iu.len, eps, true, lane, lt);
                 if (!ok) break;
             }
             first = false;
             if (RULE == ARCTE_RULE_LAZY) {  // similarity.py:106-114 / :134-142: repeated pushes, no scan
                 su = ld_state(&sr[u]);
-                while (__ddiv_rn(su.y, iu.d_in) >= eps) {
+                while (quot_ge(su.y, iu.d_in, eps)) {
                     push_node<RULE>(P, sr, touched, queue, wk, ws, u, su, iu.begin, iu.len, eps, false, lane, lt);
                     su = ld_state(&sr[u]);
                 }
@@ -252,6 +255,7 @@ k_push_threshold(const PushParams P)
 
         if (!ok) {
             // FIFO ring too small: undo and hand the seed to the retry pass
+            __syncwarp();   // the touched list was appended to by other lanes just before the abort
             for (int i = lane; i < wk.nt; i += 32) st_state(&sr[touched[i]], make_double2(0.0, 0.0));
             if (lane == 0) {
                 const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
@@ -277,7 +281,7 @@ k_push_threshold(const PushParams P)
             inside = warp_sum_i(inside) + (ld_state(&sr[seed]).x != 0.0 ? 1 : 0);
             emit = inside >= base_size;
         }
-        double tau = 0.0;
+        double tau_v = 0.0;
         if (emit) {
             double q = __ddiv_rn(ld_state(&sr[seed]).x, si.d_in);
             for (unsigned j0 = 0; j0 < si.len; j0 += 64) {
@@ -299,8 +303,9 @@ k_push_threshold(const PushParams P)
                 for (int k2 = 0; k2 < 2; ++k2)
                     if (v[k2] >= 0) q = fmin(q, __ddiv_rn(o[k2].x, d[k2]));  // arcte.py:355-356
             }
-            tau = warp_min(q);  // arcte.py:359-360
+            tau_v = warp_min(q);  // arcte.py:359-360
         }
+        const Threshold tau = make_threshold(tau_v);
         // One sweep over the touched list: count the support, keep (compacted in place, in
         // list order) the nodes with s/d_in >= tau -- arcte.py:363-367, searchsorted 'left' --
         // and zero the state (the sparse form of s[:]=0; r[:]=0, arcte.py:337-338).
@@ -328,7 +333,7 @@ k_push_threshold(const PushParams P)
                 if (x[k2] >= 0) {
                     st_state(&sr[x[k2]], make_double2(0.0, 0.0));
                     in_sup = sx[k2] != 0.0;
-                    pass = emit && in_sup && (__ddiv_rn(sx[k2], dx[k2]) >= tau);
+                    pass = emit && in_sup && quot_ge(sx[k2], dx[k2], tau);
                 }
                 support += __popc(__ballot_sync(kFull, in_sup));
                 if (emit) {
@@ -668,6 +673,9 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     P.indices = c->indices.as<int32_t>();
     P.w = c->w.as<double>();
     P.wd = c->edge_wd.as<double2>();
+    P.edge_din = c->edge_din.as<double>();
+    P.uniform_rows = c->uniform_rows ? 1 : 0;
+    P.row_w = c->row_w.as<double>();
     P.work_seed = c->work_seed.as<int32_t>();
     P.work_eps = c->work_eps.as<double>();
     P.work_ids = nullptr;
@@ -874,6 +882,9 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.indices = c->indices.as<int32_t>();
         P.w = c->w.as<double>();
         P.wd = c->edge_wd.as<double2>();
+        P.edge_din = c->edge_din.as<double>();
+        P.uniform_rows = c->uniform_rows ? 1 : 0;
+        P.row_w = c->row_w.as<double>();
         P.work_seed = c->scratch[0].as<int32_t>();
         P.work_eps = c->scratch[2].as<double>();
         P.n_work = 1;

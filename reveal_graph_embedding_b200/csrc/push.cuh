@@ -184,6 +184,36 @@ __device__ __forceinline__ double ld_weight(const double *p) { return *p; }
 enum WarpStat { WS_PUSHES = 0, WS_EDGES, WS_ENQ, WS_MAXQ, WS_SUPPORT, WS_TOUCHED, WS_SEEDDEG, WS_MEMBERS,
                 WS_EMITTED, WS_T_BEGIN, WS_COUNT };
 
+
+// `x / d >= t` as the reference evaluates it (one IEEE division, similarity.py:204, :214; arcte.py:363-367)
+// without paying for the fp64 division when a single-precision quotient already decides: the float quotient
+// is within 4e-7 of the true one (normal operands), the guard band is 1e-5, and everything inside the band,
+// denormal or out of float range goes through the exact division.  Same truth value, always.
+struct Threshold {
+    double t;
+    float lo, hi;
+};
+__device__ __forceinline__ Threshold make_threshold(double t)
+{
+    Threshold th;
+    th.t = t;
+    th.lo = __double2float_rd(t * (1.0 - 1e-5));
+    th.hi = __double2float_ru(t * (1.0 + 1e-5));
+    return th;
+}
+__device__ __forceinline__ bool quot_ge(double x, double d, const Threshold &th)
+{
+#ifndef ARCTE_NO_QUOT_FILTER
+    const float xf = __double2float_rn(x), df = __double2float_rn(d);
+    if (xf >= 1.17549435e-38f && df >= 1.17549435e-38f) {
+        const float q = __fdividef(xf, df);
+        if (q > th.hi) return true;
+        if (q < th.lo && q > 0.0f) return false;
+    }
+#endif
+    return __ddiv_rn(x, d) >= th.t;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace arcte

@@ -32,7 +32,7 @@ import numpy as np
 import scipy.sparse as sparse
 
 from ... import distributed
-from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, canonical_csr, device_count,
+from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, Engine, canonical_csr, device_count,
                        get_engine)
 
 
@@ -88,16 +88,11 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     t0 = time.perf_counter()
     run_parallel(walk)
     t1 = time.perf_counter()
-    parts = []
-    for e in engines:
-        a, b, c, d = e.segments_device()
-        parts.append((e.n_segments, e.n_members, a, b, c, d))
-
-    def assemble(rank):
-        lo, hi = distributed.row_range(n, rank, n_gpus)
-        engines[rank].assemble(parts, row_lo=lo, row_hi=hi)
-
-    run_parallel(assemble)
+    # one exchange step inside the library: NCCL all-to-all of the communities split by row block, then
+    # every GPU assembles its own rows (csrc/exchange.cu)
+    if any(e.comm_info()[:2] != (n_gpus, r) for r, e in enumerate(engines)):
+        Engine.comm_init_all(engines)
+    run_parallel(lambda rank: engines[rank].exchange_assemble())
     t2 = time.perf_counter()
     nnz = np.array([e.out_nnz for e in engines], dtype=np.int64)
     offsets = np.concatenate([[0], np.cumsum(nnz)])

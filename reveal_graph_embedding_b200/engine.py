@@ -239,6 +239,42 @@ class Engine:
         self._values_structural = True
         return nnz.value
 
+    # -- (e) multi-GPU exchange inside the library (csrc/exchange.cu) ---------------------------
+    def comm_unique_id(self):
+        """128-byte NCCL id (rank 0 creates it, the caller distributes it)."""
+        buf = C.create_string_buffer(128)
+        check(self._L.arcte_cuda_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, world, rank, unique_id):
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL id is 128 bytes")
+        check(self._L.arcte_cuda_comm_init(self._h, int(world), int(rank), C.create_string_buffer(unique_id, 128)))
+
+    def comm_info(self):
+        """(world, rank, nccl_version) of this context's communicator; world 0 = none."""
+        w, r, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self._L.arcte_cuda_comm_info(self._h, C.byref(w), C.byref(r), C.byref(v)))
+        return w.value, r.value, v.value
+
+    @staticmethod
+    def comm_init_all(engines):
+        """One process driving several GPUs: a communicator over `engines`, rank = position."""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        check(_lib.load().arcte_cuda_comm_init_all(arr, len(engines)))
+
+    def exchange_assemble(self):
+        """After extract(shard_rank = comm rank, shard_count = comm world): split the communities by
+        destination row block, all-to-all over NCCL, assemble this rank's rows.  Returns their nnz."""
+        nnz = C.c_int64(0)
+        check(self._L.arcte_cuda_exchange_assemble(self._h, C.byref(nnz)))
+        world, rank, _ = self.comm_info()
+        self.out_nnz = nnz.value
+        self.out_row_lo = (self.n * rank) // world
+        self.out_rows = (self.n * (rank + 1)) // world - self.out_row_lo
+        self._values_structural = True
+        return nnz.value
+
     def features_device(self):
         """(indptr_ptr, indices_ptr, data_ptr, n_rows, nnz) of the assembled block on the device."""
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()

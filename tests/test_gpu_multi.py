@@ -1,5 +1,5 @@
-"""Multi-GPU paths (skipped unless the box exposes >= 2 GPUs): single-process sharding over
-several contexts with peer copies, and one-process-per-GPU sharding with an NCCL all-gather."""
+"""Multi-GPU paths (skipped unless the box exposes >= 2 GPUs): one process driving several contexts and
+one process per GPU (torchrun), both through the in-library NCCL exchange (csrc/exchange.cu)."""
 import os
 import subprocess
 import sys
@@ -42,25 +42,19 @@ def test_torchrun_nccl_identical(everywhere):
 
 
 def test_in_process_multi_gpu_large_result_with_self_loops(oracle):
-    """Large result: the value array is not copied once a pre-filled block of ones is ready; the
-    2.0 entries of self-loop diagonals are patched on the host across the per-GPU row blocks."""
+    """Large result over several GPUs: the value array is written as ones by the copy threads and the 2.0
+    entries of self-loop diagonals are patched across the per-GPU row blocks."""
     if n_gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import gc
     import scipy.sparse as sparse
-    from reveal_graph_embedding_b200 import graphs, hostmem
+    from reveal_graph_embedding_b200 import graphs
     from reveal_graph_embedding_b200.embedding.arcte.arcte import arcte
     A = graphs.barabasi_albert(20000, 3, seed=2).tolil()
     for i in (0, 5, 777, 19999):
         A[i, i] = 1.0
     A = sparse.csr_matrix(A)
     want = oracle.arcte(A, RHO, EPS, 8)
-    hits0 = hostmem.counters["ones_hits"]
-    for rep in range(4):
+    for rep in range(2):
         X = arcte(A, RHO, EPS, number_of_threads=n_gpus())
         assert_csr_identical(X, want)
-        X.data[:] = -1.0
-        del X
-        gc.collect()
-        hostmem.wait_idle()
-    assert hostmem.counters["ones_hits"] > hits0
+        X.data[:] = -1.0   # the result arrays are the caller's: nothing of them is reused by the next call

@@ -26,29 +26,23 @@ for name in GOLDEN_NAMES:
         X = arcte_with_lazy_pagerank(A, RHO, EPS)
         if X is not None:
             assert_csr_identical(X, golden_features(z, 2, A.shape[0]))
-# a result large enough for the pooled page-locked buffers, with self loops: rank 0 skips the copy of
-# the value array once a block of ones is ready (hostmem.ones) and patches the 2.0 diagonals
+# a larger result with self loops: the values are written on the host, the 2.0 diagonals patched per row block
 if os.environ["ARCTE_CUDA_RESULT_ON_ALL_RANKS"] == "0":
-    import gc
     import scipy.sparse as sparse
     from oracle import arcte_oracle
-    from reveal_graph_embedding_b200 import graphs, hostmem
+    from reveal_graph_embedding_b200 import graphs
     B = graphs.barabasi_albert(20000, 3, seed=2).tolil()
     for i in (0, 5, 777, 19999):
         B[i, i] = 1.0
     B = sparse.csr_matrix(B)
     want = arcte_oracle.arcte(B, RHO, EPS, 8) if dist.get_rank() == 0 else None
-    for rep in range(4):
+    for rep in range(2):
         X = arcte(B, RHO, EPS)
         if dist.get_rank() == 0:
             assert_csr_identical(X, want)
             X.data[:] = -1.0
         del X
-        gc.collect()
-        hostmem.wait_idle()
         dist.barrier()
-    if dist.get_rank() == 0:
-        assert hostmem.counters["ones_hits"] > 0
 dist.barrier()
 if dist.get_rank() == 0:
     print("dist_check ok: world=%d, %d graphs" % (dist.get_world_size(), len(GOLDEN_NAMES)))
