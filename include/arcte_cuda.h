@@ -66,13 +66,19 @@ enum {
    discipline and arithmetic exactly (bit-identical s, r, push counts and supports); they differ in how
    the walk state is laid out and in how many queue entries one warp iteration takes. */
 enum {
-    ARCTE_ENGINE_AUTO = -1,          /* absorbing rule: BATCHED_HASH when n > 2^18, else BATCHED_DENSE;
-                                        PageRank / lazy rules: FIFO_DENSE.  Default.                      */
-    ARCTE_ENGINE_FIFO_DENSE = 0,     /* one queue entry per warp iteration, dense {s, r} array per walk     */
-    ARCTE_ENGINE_BATCHED_DENSE = 1,  /* up to 32 queue entries (64 stored entries) per warp iteration staged
-                                        in shared memory, dense {s, r} array per walk                       */
+    ARCTE_ENGINE_AUTO = -1,          /* absorbing rule: BATCHED_DENSE for 4096 <= n <= 2^19, FIFO_DENSE otherwise
+                                        (measured cross-over, profiles/r2_engines.md); PageRank / lazy rules:
+                                        FIFO_DENSE.  Default.                                              */
+    ARCTE_ENGINE_FIFO_DENSE = 0,     /* one queue entry per warp iteration, dense 16-byte {s, r} per node and walk,
+                                        32 walks per SM                                                     */
+    ARCTE_ENGINE_BATCHED_DENSE = 1,  /* up to 32 queue entries (64 stored entries) per warp iteration, all pop checks
+                                        and pushes of a batch applied at once, nodes referenced more than once
+                                        accumulated in queue order by their first reference (shared memory);
+                                        direct-mapped 32-byte {s, r, d_in, epoch} per node and walk: nothing is
+                                        ever reset; 16 walks per SM                                          */
     ARCTE_ENGINE_BATCHED_HASH = 2    /* the same batches, walk state in a growing open-addressing table of
-                                        32-byte entries per walk (one sector per touched node)              */
+                                        32-byte entries per walk (compact: the only engine whose memory does
+                                        not grow with n per walk); experimental, slowest on the shapes measured */
 };
 
 /* Counters and device timings of the last arcte_cuda_extract/assemble on this context. */
@@ -334,6 +340,12 @@ int arcte_cuda_timer_start(arcte_cuda_ctx *ctx);
 int arcte_cuda_timer_stop(arcte_cuda_ctx *ctx, double *elapsed_ms);
 /* Overwrites a scratch buffer larger than the 126 MB L2 (cold-cache timing). */
 int arcte_cuda_flush_l2(arcte_cuda_ctx *ctx);
+
+/* 64-bit content hash of the assembled block (row starts, column indices, non-unit values, each mixed with its
+   global position; terms summed modulo 2^64).  row_lo / nnz_lo: position of the block in the whole matrix, so
+   that the hashes of the row blocks of several GPUs ADD UP to the hash of the matrix one GPU assembles.
+   reveal_graph_embedding_b200.engine.csr_hash computes the same number from a scipy matrix on the host. */
+int arcte_cuda_features_hash(arcte_cuda_ctx *ctx, int64_t row_lo, int64_t nnz_lo, uint64_t *hash_out);
 
 /* -- stats ------------------------------------------------------------------- */
 int arcte_cuda_get_stats(arcte_cuda_ctx *ctx, arcte_cuda_stats *out);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
     "arcte_cuda_store_features", "arcte_cuda_store_assembled", "arcte_cuda_weighted_fold", "arcte_cuda_get_fold",
     "arcte_cuda_io_read_edge_list", "arcte_cuda_io_edge_list_copy", "arcte_cuda_io_edge_list_free", "arcte_cuda_io_write_features",
-    "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_host_fill_f64", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_get_stats",
+    "arcte_cuda_host_alloc", "arcte_cuda_host_free", "arcte_cuda_host_fill_f64", "arcte_cuda_timer_start", "arcte_cuda_timer_stop", "arcte_cuda_flush_l2", "arcte_cuda_features_hash", "arcte_cuda_get_stats",
 ]
 
 
@@ -122,6 +122,7 @@ def load():
         L.arcte_cuda_timer_start.argtypes = [vp]
         L.arcte_cuda_timer_stop.argtypes = [vp, C.POINTER(dbl)]
         L.arcte_cuda_flush_l2.argtypes = [vp]
+        L.arcte_cuda_features_hash.argtypes = [vp, i64, i64, C.POINTER(C.c_uint64)]
         L.arcte_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
         for s in SYMBOLS:
             if s not in ("arcte_cuda_last_error", "arcte_cuda_destroy", "arcte_cuda_io_edge_list_free"):

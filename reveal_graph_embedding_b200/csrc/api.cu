@@ -616,6 +616,66 @@ int arcte_cuda_features_device(arcte_cuda_ctx *c, const int64_t **dev_indptr, co
     return ARCTE_OK;
 }
 
+}  // extern "C"
+
+namespace arcte {
+// 64-bit content hash of an assembled block, additive over row blocks: every row start, column index and
+// non-unit value is mixed with its GLOBAL position (splitmix64) and the terms are summed modulo 2^64, so the
+// hashes of the row blocks of 1, 2, 4 or 8 GPUs add up to the same number exactly when the matrices agree.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256)
+k_features_hash(int64_t rows, int64_t nnz, int64_t row_lo, int64_t nnz_lo, const int64_t *__restrict__ indptr,
+                const int32_t *__restrict__ indices, const double *__restrict__ data, unsigned long long *__restrict__ out)
+{
+    unsigned long long h = 0ull;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows + nnz; i += stride) {
+        if (i < rows) {
+            h += mix64(mix64(0x1000000000000000ull + (unsigned long long)(row_lo + i)) + (unsigned long long)(indptr[i] + nnz_lo));
+        } else {
+            const int64_t k = i - rows;
+            const unsigned long long pos = (unsigned long long)(nnz_lo + k);
+            h += mix64(mix64(0x2000000000000000ull + pos) + (unsigned long long)(uint32_t)indices[k]);
+            const double v = data[k];
+            if (v != 1.0) h += mix64(mix64(0x3000000000000000ull + pos) + (unsigned long long)__double_as_longlong(v));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(kFull, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
+}  // namespace arcte
+
+extern "C" {
+
+int arcte_cuda_features_hash(arcte_cuda_ctx *c, int64_t row_lo, int64_t nnz_lo, uint64_t *hash_out)
+{
+    CHECK_CTX(c);
+    if (!c->have_features || !hash_out) { set_error("features_hash: call assemble first"); return ARCTE_E_ARG; }
+    ARCTE_TRY(dev_reserve(c->scratch[4], sizeof(unsigned long long) * 2));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(c->scratch[4].p, 0, sizeof(unsigned long long), c->stream));
+    const int64_t items = c->out_rows + c->out_nnz;
+    unsigned grid = (unsigned)((items + 255) / 256);
+    if (grid > (unsigned)c->sm_count * 16) grid = (unsigned)c->sm_count * 16;
+    if (grid < 1) grid = 1;
+    k_features_hash<<<grid, 256, 0, c->stream>>>(c->out_rows, c->out_nnz, row_lo, nnz_lo, c->out_indptr.as<int64_t>(),
+                                                 c->out_indices.as<int32_t>(), c->out_data.as<double>(),
+                                                 c->scratch[4].as<unsigned long long>());
+    ++c->stats.launches;
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0ull;
+    ARCTE_CUDA_TRY(cudaMemcpyAsync(&h, c->scratch[4].p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *hash_out = h;
+    return ARCTE_OK;
+}
+
 int arcte_cuda_get_stats(arcte_cuda_ctx *c, arcte_cuda_stats *out)
 {
     if (!c || !out) { set_error("get_stats: null argument"); return ARCTE_E_ARG; }

@@ -35,6 +35,18 @@ struct Walk {
     int nt;                // touched count
 };
 
+// Experiment switches of the one-entry-per-iteration kernel, both measured as losses on the bench shapes and off
+// (profiles/r2_fifo_variants.md):
+//   ARCTE_FIFO_UNIFORM   rows of one repeated transition weight: one product per push, no weight loads
+//                        (the extra gather of the row weight costs more than the coalesced weight loads: +5 %)
+//   ARCTE_FIFO_EDGE_DIN  in-degree of the target read coalesced with the row instead of gathered per neighbour
+//                        (the gathers mostly hit L2, the extra 8 bytes per stored entry do not: +4 %)
+#ifndef ARCTE_FIFO_UNIFORM
+#define ARCTE_FIFO_UNIFORM 0
+#endif
+#ifndef ARCTE_FIFO_EDGE_DIN
+#define ARCTE_FIFO_EDGE_DIN 0
+#endif
 #ifndef ARCTE_PUSH_UNROLL
 #define ARCTE_PUSH_UNROLL 1
 #endif
@@ -78,9 +90,16 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
 #endif
     // every row of an unweighted graph holds one repeated transition weight (transition.cu: k_row_uniform):
     // one product per push instead of one weight load per stored entry
+#if ARCTE_FIFO_UNIFORM
     const bool uni = P.uniform_rows != 0;
     const double p_uni = uni ? __dmul_rn(c, P.row_w[u]) : 0.0;
+#else
+    const bool uni = false;
+    const double p_uni = 0.0;
+#endif
+#if ARCTE_FIFO_EDGE_DIN
     const double *__restrict__ edin = P.edge_din + begin;   // in-degree of every entry's target, coalesced
+#endif
     for (unsigned base = 0; base < len; base += 32 * kPushUnroll) {
         // phase 1: neighbour ids, transition weights and target in-degrees of up to kPushUnroll chunks
         int v[kPushUnroll];
@@ -98,7 +117,9 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
                 dv[k] = e.y;
 #else
                 p[k] = uni ? p_uni : __dmul_rn(c, ld_weight(wgt + j));
+#if ARCTE_FIFO_EDGE_DIN
                 dv[k] = edin[j];
+#endif
 #endif
             }
         }
@@ -108,6 +129,9 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
         for (int k = 0; k < kPushUnroll; ++k) {
             if (v[k] >= 0) {
                 o[k] = ld_state(&sr[v[k]]);
+#if !ARCTE_EDGE_RECORDS && !ARCTE_FIFO_EDGE_DIN
+                dv[k] = ld_info_din(&P.info[v[k]]);
+#endif
             }
         }
         // phase 3: update and store (neighbours of one node are distinct: no ordering needed)
@@ -575,7 +599,10 @@ static int resolve_engine(const arcte_cuda_ctx *c, int rule)
         else if (env && !strcmp(env, "dense")) e = ARCTE_ENGINE_BATCHED_DENSE;
         else if (env && !strcmp(env, "hash")) e = ARCTE_ENGINE_BATCHED_HASH;
     }
-    if (e == ARCTE_ENGINE_AUTO) e = c->n > (int64_t(1) << 18) ? ARCTE_ENGINE_BATCHED_HASH : ARCTE_ENGINE_BATCHED_DENSE;
+    // measured (profiles/r2_engines.md): the batched direct-mapped engine wins on medium graphs (Flickr shape 134
+    // vs 166 ms, BA(150000,3) 14.6 vs 19.7 ms); tiny graphs and the 1.1 M-node bench shape go to the FIFO engine
+    if (e == ARCTE_ENGINE_AUTO)
+        e = (c->n >= 4096 && c->n <= (int64_t(1) << 19)) ? ARCTE_ENGINE_BATCHED_DENSE : ARCTE_ENGINE_FIFO_DENSE;
     return e;
 }
 

@@ -62,6 +62,33 @@ def canonical_csr(adjacency_matrix):
     return A
 
 
+def _mix64(x):
+    x = x + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def csr_hash(X, chunk=1 << 24):
+    """The number arcte_cuda_features_hash gives for the same matrix, computed on the host from a scipy CSR:
+    sum modulo 2^64 of splitmix64 terms over the row starts, the column indices and the values other than 1.0,
+    each mixed with its position."""
+    with np.errstate(over="ignore"):
+        h = np.uint64(0)
+        n, nnz = X.shape[0], int(X.indptr[-1])
+        for lo in range(0, n, chunk):
+            i = np.arange(lo, min(n, lo + chunk), dtype=np.uint64)
+            h += _mix64(_mix64(np.uint64(0x1000000000000000) + i) + X.indptr[lo:lo + i.size].astype(np.uint64)).sum(dtype=np.uint64)
+        for lo in range(0, nnz, chunk):
+            k = np.arange(lo, min(nnz, lo + chunk), dtype=np.uint64)
+            h += _mix64(_mix64(np.uint64(0x2000000000000000) + k) + X.indices[lo:lo + k.size].astype(np.uint64)).sum(dtype=np.uint64)
+            v = X.data[lo:lo + k.size]
+            m = v != 1.0
+            if m.any():
+                h += _mix64(_mix64(np.uint64(0x3000000000000000) + k[m]) + v[m].view(np.uint64)).sum(dtype=np.uint64)
+        return int(h)
+
+
 class Engine:
     def __init__(self, device=0):
         self._L = _lib.load()
@@ -274,6 +301,13 @@ class Engine:
         self.out_rows = (self.n * (rank + 1)) // world - self.out_row_lo
         self._values_structural = True
         return nnz.value
+
+    def features_hash(self, nnz_lo=0):
+        """64-bit content hash of the assembled block (include/arcte_cuda.h); nnz_lo: stored entries of the row
+        blocks before this one.  Hashes of row blocks add up (mod 2^64) to csr_hash() of the whole matrix."""
+        h = C.c_uint64(0)
+        check(self._L.arcte_cuda_features_hash(self._h, int(getattr(self, "out_row_lo", 0)), int(nnz_lo), C.byref(h)))
+        return int(h.value)
 
     def features_device(self):
         """(indptr_ptr, indices_ptr, data_ptr, n_rows, nnz) of the assembled block on the device."""

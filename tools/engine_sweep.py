@@ -26,16 +26,18 @@ eng = Engine(0)
 t = time.time()
 eng.set_graph(A)
 print("set_graph %.3fs n=%d nnz=%d" % (time.time() - t, A.shape[0], A.nnz), flush=True)
-for name, wps in configs:
+for cfg in configs:
+    name, wps = cfg[0], cfg[1]
+    mem_pct = int(cfg[2]) if len(cfg) > 2 else 0       # engine:warps_per_sm[:mem_percent]
     eng.set_engine(name)
-    eng.configure(warps_per_sm=int(wps))
+    eng.configure(warps_per_sm=int(wps), mem_percent=mem_pct)
     for rep in range(2):
         t = time.time()
         eng.extract(0, RHO, EPS)
         dt = time.time() - t
     st = eng.stats()
     seg_seed, seg_cnt, seg_off, mem = eng.segments()
-    line = {"workload": workload, "engine": name, "wps": int(wps), "slots": st["n_slots"],
+    line = {"workload": workload, "engine": name, "wps": int(wps), "mem_percent": mem_pct, "slots": st["n_slots"],
             "ms_push": round(st["ms_push"], 3), "extract_wall_ms": round(dt * 1e3, 1),
             "util": round(st["slot_utilisation"], 3),
             "GBps_alg": round(st["alg_bytes_push"] / st["ms_push"] / 1e6, 1),
