@@ -227,6 +227,12 @@ int arcte_cuda_fetch_features(arcte_cuda_ctx *ctx, int64_t *host_indptr, int32_t
 int arcte_cuda_features_device(arcte_cuda_ctx *ctx, const int64_t **dev_indptr, const int32_t **dev_indices,
                                const double **dev_data, int64_t *n_rows, int64_t *nnz);
 
+/* -- f3: the centrality of arcte_and_centrality (embedding/arcte/cython_opt/arcte.pyx:125-241) ----------
+   centrality[x] = sum over ALL nodes taken as seeds of s_seed[x] / d_in[x] with the RAW epsilon (arcte.pyx:164,
+   :183-191).  Accumulated in 2^-38 fixed point (deterministic); the reference adds in seed order in floating
+   point, so the two agree to about n * 2^-39 + rounding, far inside the push error bound. */
+int arcte_cuda_centrality(arcte_cuda_ctx *ctx, double rho, double epsilon, double *host_centrality);
+
 /* -- e: the multi-GPU exchange, inside the library (arcte.py:650-673) ------------------------
    Rank r of `world` walks shard r (arcte_cuda_extract with shard_rank = r, shard_count = world) and owns the
    rows [n r / world, n (r+1) / world) of the result.  arcte_cuda_exchange_assemble splits every community by

@@ -22,7 +22,7 @@ SYMBOLS = [
     "arcte_cuda_device_count", "arcte_cuda_create", "arcte_cuda_destroy", "arcte_cuda_last_error", "arcte_cuda_configure", "arcte_cuda_set_schedule", "arcte_cuda_set_engine",
     "arcte_cuda_set_graph", "arcte_cuda_set_transition", "arcte_cuda_set_seeds", "arcte_cuda_build_transition", "arcte_cuda_get_transition",
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
-    "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_get_segments",
+    "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_centrality", "arcte_cuda_get_segments",
     "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features", "arcte_cuda_fetch_features",
     "arcte_cuda_comm_unique_id", "arcte_cuda_comm_init", "arcte_cuda_comm_init_all", "arcte_cuda_comm_info", "arcte_cuda_exchange_assemble",
     "arcte_cuda_normalize_columns", "arcte_cuda_normalize_features", "arcte_cuda_chi2_contingency", "arcte_cuda_peak_snr",
@@ -86,6 +86,7 @@ def load():
         L.arcte_cuda_epsilon_effective.argtypes = [vp, dbl, i64, vp, vp]
         L.arcte_cuda_push.argtypes = [vp, i32, i64, dbl, dbl, vp, vp, C.POINTER(i64)]
         L.arcte_cuda_extract.argtypes = [vp, i32, dbl, dbl, i32, i32, vp, C.POINTER(i64), C.POINTER(i64)]
+        L.arcte_cuda_centrality.argtypes = [vp, dbl, dbl, vp]
         L.arcte_cuda_get_segments.argtypes = [vp, vp, vp, vp, vp]
         L.arcte_cuda_segments_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.arcte_cuda_export_segments.argtypes = [vp, vp, vp, vp, vp]

@@ -64,6 +64,19 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
 
 }  // namespace arcte
 
+namespace arcte {
+__global__ void k_iota(int64_t n, int32_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+__global__ void k_cent_finish(int64_t n, const unsigned long long *acc, double inv_scale, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __dmul_rn(__ull2double_rn(acc[i]), inv_scale);
+}
+}  // namespace arcte
+
 using namespace arcte;
 
 #define CHECK_CTX(ctx)                                   \
@@ -422,6 +435,42 @@ int arcte_cuda_extract(arcte_cuda_ctx *c, int rule, double rho, double epsilon, 
     if (n_segments) *n_segments = c->n_segments;
     if (n_members) *n_members = c->n_members;
     return ARCTE_OK;
+}
+
+
+/* The RCT centrality of arcte_and_centrality (embedding/arcte/cython_opt/arcte.pyx:125-241): every node is a
+   seed (out_degree != 0 holds for all of them after transition.py:58), the walk uses the RAW epsilon (no
+   epsilon-effective, arcte.pyx:164), and centrality[x] = sum over seeds of s[x] / d_in[x] (arcte.pyx:183-191). */
+int arcte_cuda_centrality(arcte_cuda_ctx *c, double rho, double epsilon, double *host_centrality)
+{
+    CHECK_CTX(c);
+    if (!c->have_transition || !host_centrality) { set_error("centrality: no graph / null output"); return ARCTE_E_ARG; }
+    const int64_t n = c->n;
+    const int64_t saved_seeds = c->n_seeds;
+    DevBuf acc, eps;
+    int rc = dev_reserve(acc, sizeof(unsigned long long) * (size_t)n);
+    if (rc == ARCTE_OK) rc = dev_reserve(eps, sizeof(double) * (size_t)n);
+    std::vector<double> h_eps((size_t)n, epsilon);
+    if (rc == ARCTE_OK) {
+        cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long) * (size_t)n, c->stream);
+        k_iota<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->seeds.as<int32_t>());   // every node, ascending
+        c->n_seeds = n;
+        c->centrality_acc = acc.as<unsigned long long>();
+        rc = extract_shard(c, ARCTE_RULE_ABSORBING, rho, epsilon, 0, 1, h_eps.data());
+        c->centrality_acc = nullptr;
+    }
+    if (rc == ARCTE_OK) {
+        k_cent_finish<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, acc.as<unsigned long long>(), 1.0 / 274877906944.0,
+                                                                         eps.as<double>());
+        rc = copy_to_host(c, host_centrality, eps.p, sizeof(double) * (size_t)n);
+    }
+    dev_free(acc);
+    dev_free(eps);
+    // back to the seed list of arcte() (arcte.py:610-617); the segments of the centrality walk are not kept
+    c->n_seeds = saved_seeds;
+    c->have_segments = c->have_features = false;
+    const int rc2 = select_seeds(c);
+    return rc != ARCTE_OK ? rc : rc2;
 }
 
 int arcte_cuda_get_segments(arcte_cuda_ctx *c, int32_t *host_seg_seed, int32_t *host_seg_count,

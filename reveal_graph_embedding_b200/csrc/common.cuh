@@ -171,6 +171,7 @@ struct arcte_cuda_ctx {
     int64_t n_segments = 0, n_members = 0, member_cap = 0;
     bool have_segments = false;
 
+    unsigned long long *centrality_acc = nullptr;  // set by arcte_cuda_centrality for the duration of its extraction
     arcte::SlotPool slots;
     arcte::BatchedPool bpool;
     arcte::DevBuf row_w;       // double [n]  the repeated transition weight of each row (uniform_rows)

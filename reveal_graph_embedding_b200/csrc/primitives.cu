@@ -144,11 +144,15 @@ int exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, DevBuf &scrat
 //   pass = histogram kernel -> exclusive scan of hist[digit][tile] -> scatter kernel.
 // Stability inside a tile: each warp owns a contiguous sub-tile and walks it in index
 // order 32 elements at a time; __match_any_sync ranks equal digits by lane.
+// The scatter kernel first REORDERS the tile in shared memory (digit-major, tile order kept
+// inside a digit) and then writes it out front to back: consecutive threads write consecutive
+// addresses of one digit's global run, whole sectors at a time.  (Round 1 let every lane store
+// its pair straight to its own global position: 510 GB/s on 517 M pairs, profiles/r2_k5_sort.md.)
 // ------------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
+constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortRounds = 16;                          // 32-element rounds per warp
-constexpr int kSortTile = kSortWarps * kSortRounds * 32; // 4096
+constexpr int kSortTile = kSortWarps * kSortRounds * 32; // 8192
 constexpr int kDigits = 256;
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -156,7 +160,7 @@ k_radix_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, int64_t n_
              int32_t *__restrict__ hist)
 {
     __shared__ int32_t sh[kDigits];
-    sh[threadIdx.x] = 0;
+    if (threadIdx.x < kDigits) sh[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
 #pragma unroll 4
@@ -165,8 +169,16 @@ k_radix_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, int64_t n_
         if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & 0xff], 1);
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+    if (threadIdx.x < kDigits) hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
 }
+
+template <typename V> struct SortShared {
+    uint32_t key[kSortTile];
+    V val[kSortTile];
+    int32_t woff[kSortWarps][kDigits + 1];   // per warp and digit: count, then local start
+    int32_t dstart[kDigits + 1];             // local start of every digit in the reordered tile
+    int64_t gbase[kDigits];                  // global start of (digit, tile) minus dstart[digit]
+};
 
 template <typename V>
 __global__ void __launch_bounds__(kSortThreads)
@@ -174,14 +186,16 @@ k_radix_scatter(const uint32_t *__restrict__ keys, const V *__restrict__ vals, i
                 int64_t n_tiles, const int64_t *__restrict__ hist_prefix,
                 uint32_t *__restrict__ keys_out, V *__restrict__ vals_out)
 {
-    __shared__ int64_t woff[kSortWarps][kDigits + 1];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortShared<V> &S = *reinterpret_cast<SortShared<V> *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    for (int i = threadIdx.x; i < kSortWarps * (kDigits + 1); i += kSortThreads)
-        (&woff[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kSortWarps * (kDigits + 1); i += kSortThreads) (&S.woff[0][0])[i] = 0;
     __syncthreads();
 
-    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * (kSortRounds * 32);
+    const int64_t tbase = (int64_t)blockIdx.x * kSortTile;
+    const int64_t wbase = tbase + (int64_t)warp * (kSortRounds * 32);
+    const int tile_n = (int)((n - tbase) < (int64_t)kSortTile ? (n - tbase) : (int64_t)kSortTile);
     uint32_t key[kSortRounds];
     // sweep 1: per-warp digit counts
 #pragma unroll
@@ -191,38 +205,67 @@ k_radix_scatter(const uint32_t *__restrict__ keys, const V *__restrict__ vals, i
         key[r] = valid ? keys[idx] : 0u;
         const int d = valid ? (int)((key[r] >> shift) & 0xff) : kDigits;
         const unsigned peers = __match_any_sync(kFull, d);
-        if ((peers & lt) == 0) woff[warp][d] += __popc(peers);
+        if ((peers & lt) == 0) S.woff[warp][d] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-    // per digit: global start of (digit, tile) + counts of the warps before
-    {
-        const int d = threadIdx.x;
-        int64_t run = hist_prefix[(int64_t)d * n_tiles + blockIdx.x];
+    // per digit: totals of the tile -> exclusive scan over the digits -> per-warp local starts
+    int total = 0;
+    if (threadIdx.x < kDigits) {
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const int64_t c = woff[w][d];
-            woff[w][d] = run;
-            run += c;
+        for (int w = 0; w < kSortWarps; ++w) total += S.woff[w][threadIdx.x];
+    }
+    {   // exclusive scan of `total` over threads 0..255 (8 warps)
+        int incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (threadIdx.x < kDigits && lane == 31) S.dstart[warp] = incl;   // warp sums, parked in dstart[0..7]
+        __syncthreads();
+        int before = 0;
+        if (threadIdx.x < kDigits)
+            for (int w = 0; w < warp; ++w) before += S.dstart[w];
+        __syncthreads();
+        if (threadIdx.x < kDigits) {
+            const int start = before + incl - total;
+            S.dstart[threadIdx.x] = start;
+            S.gbase[threadIdx.x] = hist_prefix[(int64_t)threadIdx.x * n_tiles + blockIdx.x] - start;
+            int run = start;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const int c = S.woff[w][threadIdx.x];
+                S.woff[w][threadIdx.x] = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
-    // sweep 2: stable scatter
+    // sweep 2: stable reorder of the tile in shared memory
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < n;
         const int d = valid ? (int)((key[r] >> shift) & 0xff) : kDigits;
         const unsigned peers = __match_any_sync(kFull, d);
-        const int64_t start = woff[warp][d];
+        const int start = S.woff[warp][d];
         __syncwarp();
-        if ((peers & lt) == 0) woff[warp][d] = start + __popc(peers);
+        if ((peers & lt) == 0) S.woff[warp][d] = start + __popc(peers);
         __syncwarp();
         if (valid) {
-            const int64_t dst = start + __popc(peers & lt);
-            keys_out[dst] = key[r];
-            vals_out[dst] = vals[idx];
+            const int pos = start + __popc(peers & lt);
+            S.key[pos] = key[r];
+            S.val[pos] = vals[idx];
         }
+    }
+    __syncthreads();
+    // write the reordered tile front to back: runs of one digit go to consecutive global addresses
+    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
+        const uint32_t k = S.key[i];
+        const int64_t dst = S.gbase[(k >> shift) & 0xff] + i;
+        keys_out[dst] = k;
+        vals_out[dst] = S.val[i];
     }
 }
 
@@ -237,6 +280,13 @@ int radix_sort_pairs(uint32_t *k0, void *v0, uint32_t *k1, void *v1, int64_t n, 
     const int64_t hist_n = n_tiles * kDigits;
     ARCTE_TRY(dev_reserve(scratch_hist, (size_t)hist_n * sizeof(int32_t)));
     ARCTE_TRY(dev_reserve(scratch_scan, (size_t)(hist_n + 1) * sizeof(int64_t)));
+    // more than 48 KB of dynamic shared memory needs the opt-in (per device: set on every call, it is cheap)
+    if (value_bytes == 4)
+        ARCTE_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(SortShared<uint32_t>)));
+    else
+        ARCTE_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(SortShared<uint64_t>)));
     uint32_t *ki = k0, *ko = k1;
     void *vi = v0, *vo = v1;
     bool second = false;
@@ -247,11 +297,11 @@ int radix_sort_pairs(uint32_t *k0, void *v0, uint32_t *k1, void *v1, int64_t n, 
         ARCTE_TRY(exclusive_scan_i32(scratch_hist.as<int32_t>(), scratch_scan.as<int64_t>(),
                                      hist_n, scratch_scan2, stream, launches));
         if (value_bytes == 4)
-            k_radix_scatter<uint32_t><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+            k_radix_scatter<uint32_t><<<(unsigned)n_tiles, kSortThreads, sizeof(SortShared<uint32_t>), stream>>>(
                 ki, (const uint32_t *)vi, n, shift, n_tiles, scratch_scan.as<int64_t>(), ko,
                 (uint32_t *)vo);
         else
-            k_radix_scatter<uint64_t><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+            k_radix_scatter<uint64_t><<<(unsigned)n_tiles, kSortThreads, sizeof(SortShared<uint64_t>), stream>>>(
                 ki, (const uint64_t *)vi, n, shift, n_tiles, scratch_scan.as<int64_t>(), ko,
                 (uint64_t *)vo);
         ++*launches;

@@ -358,6 +358,10 @@ k_push_threshold(const PushParams P)
                     st_state(&sr[x[k2]], make_double2(0.0, 0.0));
                     in_sup = sx[k2] != 0.0;
                     pass = emit && in_sup && quot_ge(sx[k2], dx[k2], tau);
+                    // arcte.pyx:164-191: centrality += s / d_in over the support of every seed, in 2^-38 fixed
+                    // point so that the sum does not depend on the order the seeds finish in
+                    if (P.centrality && in_sup)
+                        atomicAdd(&P.centrality[x[k2]], __double2ull_rn(__dmul_rn(__ddiv_rn(sx[k2], dx[k2]), P.cent_scale)));
                 }
                 support += __popc(__ballot_sync(kFull, in_sup));
                 if (emit) {
@@ -665,8 +669,12 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         return ARCTE_E_ARG;
     }
     int64_t n_slots = 0, qcap = 0;
-    const int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
+    const int engine = (frontier || c->centrality_acc) ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
     const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
+    if (c->centrality_acc && (frontier || rule != ARCTE_RULE_ABSORBING)) {
+        set_error("centrality: absorbing rule, FIFO schedule only");
+        return ARCTE_E_ARG;
+    }
     release_other_pools(c, batched, engine);
     if (frontier) {
         ARCTE_TRY(frontier_plan_slots(c, S, &n_slots));
@@ -727,6 +735,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.inv_scale = 1.0 / P.scale;
     }
     if (batched) batched_fill_params(c, engine, P);
+    P.centrality = c->centrality_acc;
+    P.cent_scale = 274877906944.0;   // 2^38
 
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
     ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.as<int64_t>() + PC_T_START, 0xff, sizeof(int64_t), st));

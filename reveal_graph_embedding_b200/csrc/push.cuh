@@ -65,6 +65,8 @@ struct PushParams {
     int64_t tbl_cap_max;       // entries per half, power of two
     int32_t *tbl_clean;        // [n_slots][2] entries of each half known to be all-EMPTY from index 0
     double *dbg_s, *dbg_r;     // operator seam: dense s / r of the single walked seed (pre-zeroed)
+    unsigned long long *centrality;   // [n] fixed-point sum over seeds of s/d_in (arcte_and_centrality), or nullptr
+    double cent_scale;                // 2^38
     const double *edge_din;    // [nnz] in-degree of the target of every stored entry
     int uniform_rows;          // 1: every row of w holds one repeated value, kept in row_w
     const double *row_w;       // [n] that value (uniform_rows)

@@ -141,6 +141,29 @@ def arcte_with_lazy_pagerank(adjacency_matrix, rho, epsilon, number_of_threads=N
     return _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, RULE_LAZY)
 
 
+def arcte_and_centrality(adjacency_matrix, rho, epsilon):
+    """The reference's Cython-only variant (embedding/arcte/cython_opt/arcte.pyx:125-241): ARCTE features plus
+    the RCT centrality vector.
+
+    centrality[x] = sum over ALL nodes taken as seeds of s_seed[x] / in_degree[x], the walks run with the RAW
+    epsilon (arcte.pyx:164, :183-191; nodes without out-edges get 1.0, :222 -- none after transition.py:58).
+    It is computed on the GPU in 2^-38 fixed point (deterministic) and agrees with a restatement of those lines
+    to ~1e-9 relative (tests/test_gpu_parity.py::test_centrality_vs_restatement).
+
+    The feature half of that function is NOT reproduced: it numbers communities compactly in an order that
+    depends on an unstable argsort of tied values (arcte.pyx:194-212), its `centrality += s_sparse` no longer
+    type-checks under current scipy, and its build is commented out in the reference's setup.py:4-12, so
+    there is no runnable behaviour to be identical to.  The features returned here are arcte()'s (arcte.py:591),
+    which is what the reference's console script and experiments use."""
+    A = canonical_csr(adjacency_matrix)
+    eng = get_engine(0)
+    eng.set_graph(A, canonical=True)
+    centrality = eng.centrality(rho, epsilon)
+    eng.extract(RULE_ABSORBING, rho, epsilon)
+    eng.assemble()
+    return eng.features(), centrality
+
+
 def _worker(rule, iterate_nodes, indices_c, indptr_c, data_c, out_degree, in_degree, rho, epsilon):
     eng = get_engine(0)
     eng.set_transition(indptr_c, indices_c, data_c, out_degree, in_degree)

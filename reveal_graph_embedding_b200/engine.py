@@ -223,6 +223,13 @@ class Engine:
         self.n_segments, self.n_members = ns.value, nm.value
         return ns.value, nm.value
 
+    def centrality(self, rho, epsilon):
+        """RCT centrality of arcte_and_centrality (cython_opt/arcte.pyx:125-241) for the uploaded graph: sum over
+        all nodes taken as seeds of s/d_in, raw epsilon.  float64 [n]."""
+        out = np.empty(self.n, dtype=np.float64)
+        check(self._L.arcte_cuda_centrality(self._h, float(rho), float(epsilon), ptr(out)))
+        return out
+
     def segments(self):
         S, M = self.n_segments, self.n_members
         seed = np.empty(max(S, 1), dtype=np.int32)
