@@ -328,6 +328,18 @@ int arcte_cuda_io_write_features(const char *path, const char *separator, int64_
                                  const int32_t *indices, const double *data, const int64_t *node_ids,
                                  int n_threads, int64_t *bytes_written);
 
+/* One process per GPU: the same copy with the destination arrays living in ANOTHER process (`pid`, e.g. rank 0 of
+   a torchrun job; the three pointers are virtual addresses of that process).  The pinned slots are written there
+   with process_vm_writev, so every rank brings its own row block home through its own PCIe link and nothing is
+   staged in shared memory.  Needs ptrace permission on the target (same user, Yama scope <= 1); pid = own pid or
+   0 is the local copy.  arcte_cuda_host_write_to copies a small host buffer the same way;
+   arcte_cuda_host_advise_huge asks for huge pages for a range of THIS process (the owner of the destination
+   calls it before the first touch). */
+int arcte_cuda_fetch_features_to(arcte_cuda_ctx *ctx, int64_t pid, int64_t *dst_indptr, int32_t *dst_indices,
+                                 double *dst_data, int values_are_ones, int n_threads);
+int arcte_cuda_host_write_to(int64_t pid, void *dst, const void *src, int64_t bytes);
+int arcte_cuda_host_advise_huge(void *p, int64_t bytes);
+
 /* -- page-locked host memory for results ------------------------------------- */
 /* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be
    page-locked so the device-to-host copy runs at PCIe rate instead of through the

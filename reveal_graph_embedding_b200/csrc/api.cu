@@ -609,6 +609,26 @@ int arcte_cuda_fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *
     return fetch_features(c, host_indptr, host_indices, host_data, values_are_ones, n_threads);
 }
 
+int arcte_cuda_fetch_features_to(arcte_cuda_ctx *c, int64_t pid, int64_t *dst_indptr, int32_t *dst_indices, double *dst_data,
+                                 int values_are_ones, int n_threads)
+{
+    CHECK_CTX(c);
+    if (!c->have_features) { set_error("fetch_features_to: call assemble first"); return ARCTE_E_ARG; }
+    return fetch_features(c, dst_indptr, dst_indices, dst_data, values_are_ones, n_threads, (long)pid);
+}
+
+int arcte_cuda_host_write_to(int64_t pid, void *dst, const void *src, int64_t bytes)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) { set_error("host_write_to: bad arguments"); return ARCTE_E_ARG; }
+    return host_write_remote((long)pid, dst, src, (size_t)bytes);
+}
+
+int arcte_cuda_host_advise_huge(void *p, int64_t bytes)
+{
+    if (p && bytes > 0) host_advise_huge(p, (size_t)bytes);
+    return ARCTE_OK;
+}
+
 int arcte_cuda_host_alloc(void **out, int64_t bytes)
 {
     if (!out || bytes <= 0) { set_error("host_alloc: bad arguments"); return ARCTE_E_ARG; }

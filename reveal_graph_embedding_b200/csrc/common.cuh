@@ -106,7 +106,9 @@ struct HostRing {
 int copy_to_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);
 int copy_from_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);
 int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data, int values_are_ones,
-                   int n_threads);
+                   int n_threads, long pid = 0);
+int host_write_remote(long pid, void *remote_dst, const void *local_src, size_t bytes);
+void host_advise_huge(void *p, size_t bytes);
 void free_ring(arcte_cuda_ctx *c);
 void comm_free(arcte_cuda_ctx *c);
 

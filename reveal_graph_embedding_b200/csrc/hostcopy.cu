@@ -9,6 +9,8 @@
 // chunk is in flight.  The first touch of the destination pages (a fresh numpy array is untouched
 // memory) is thereby spread over all the threads as well, and the range is advised to use huge pages.
 #include <sys/mman.h>
+#include <sys/uio.h>
+#include <errno.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -91,8 +93,27 @@ struct CopyJob {
     bool to_host;
 };
 
+// Destination process of a device -> host job: 0 = this one (memcpy); otherwise the host addresses are virtual
+// addresses of THAT process and the pinned slot is written there with process_vm_writev (one process per GPU:
+// every rank streams its rows straight into the result arrays of rank 0 through its own PCIe link).
+static bool put(pid_t pid, void *dst, const void *src, size_t len)
+{
+    if (pid == 0) {
+        memcpy(dst, src, len);
+        return true;
+    }
+    size_t done = 0;
+    while (done < len) {
+        struct iovec l = {(char *)const_cast<void *>(src) + done, len - done}, r = {(char *)dst + done, len - done};
+        const ssize_t k = process_vm_writev(pid, &l, 1, &r, 1, 0);
+        if (k <= 0) return false;
+        done += (size_t)k;
+    }
+    return true;
+}
+
 static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double *fill, size_t fill_count, double fill_value,
-                    int n_threads)
+                    int n_threads, pid_t pid = 0)
 {
     struct Chunk { int job; size_t off, len; };   // job == -1: fill
     std::vector<Chunk> copies, fills, chunks;
@@ -110,9 +131,13 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
     int T = host_threads(n_threads);
     if ((size_t)T > chunks.size()) T = (int)chunks.size();
     ARCTE_TRY(ensure_ring(c, T));
-    for (const CopyJob &j : jobs)
-        if (j.to_host) advise_huge(j.host, j.bytes);
-    if (fill) advise_huge(fill, fill_bytes);
+    if (pid == 0) {
+        for (const CopyJob &j : jobs)
+            if (j.to_host) advise_huge(j.host, j.bytes);
+        if (fill) advise_huge(fill, fill_bytes);
+    }
+    std::vector<double> fill_src;   // remote fills copy from a local block of the value
+    if (pid != 0 && fill) fill_src.assign(kSlotBytes / sizeof(double), fill_value);
     // interleave copy and fill chunks so that every thread sees both kinds
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
@@ -127,7 +152,7 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
         auto drain = [&]() {
             if (pending_slot < 0) return;
             if (cudaEventSynchronize(r.events[2 * t + pending_slot]) != cudaSuccess) failed = 1;
-            memcpy(jobs[pending.job].host + pending.off, slot[pending_slot], pending.len);
+            if (!put(pid, jobs[pending.job].host + pending.off, slot[pending_slot], pending.len)) failed = 2;
             pending_slot = -1;
         };
         for (;;) {
@@ -136,7 +161,8 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
             const Chunk ch = chunks[i];
             if (ch.job < 0) {
                 double *p = (double *)((char *)fill + ch.off);
-                std::fill(p, p + ch.len / sizeof(double), fill_value);
+                if (pid == 0) std::fill(p, p + ch.len / sizeof(double), fill_value);
+                else if (!put(pid, p, fill_src.data(), ch.len)) failed = 2;
                 continue;
             }
             const CopyJob &jb = jobs[ch.job];
@@ -155,7 +181,7 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
                 pending_slot = s;
                 if (prev_slot >= 0 && prev_slot != s) {   // copy the previous chunk out while this one is in flight
                     if (cudaEventSynchronize(r.events[2 * t + prev_slot]) != cudaSuccess) failed = 1;
-                    memcpy(jobs[prev.job].host + prev.off, slot[prev_slot], prev.len);
+                    if (!put(pid, jobs[prev.job].host + prev.off, slot[prev_slot], prev.len)) failed = 2;
                 }
             } else {
                 drain();
@@ -178,7 +204,9 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
     for (std::thread &th : pool) th.join();
     if (failed) {
         (void)cudaGetLastError();
-        set_error("streamed host copy failed");
+        set_error(failed == 2 ? std::string("streamed host copy: process_vm_writev into process ") + std::to_string((long)pid) +
+                                    " failed (" + strerror(errno) + ")"
+                              : std::string("streamed host copy failed"));
         return ARCTE_E_CUDA;
     }
     return ARCTE_OK;
@@ -217,7 +245,7 @@ int copy_from_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes)
 // the self-loop diagonals it patches itself, arcte.py:379-381, :676-679) -- written as ones by the same
 // threads while the indices stream in, which saves two thirds of the PCIe bytes.
 int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indices, double *host_data, int values_are_ones,
-                   int n_threads)
+                   int n_threads, long pid)
 {
     ARCTE_CUDA_TRY(cudaStreamSynchronize(c->stream));
     std::vector<CopyJob> jobs;
@@ -229,7 +257,18 @@ int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indice
         if (values_are_ones) fill = host_data;
         else jobs.push_back({(char *)host_data, c->out_data.as<char>(), sizeof(double) * nnz, true});
     }
-    return run_jobs(c, jobs, fill, fill ? nnz : 0, 1.0, n_threads);
+    return run_jobs(c, jobs, fill, fill ? nnz : 0, 1.0, n_threads, (pid_t)(pid == (long)getpid() ? 0 : pid));
 }
+
+int host_write_remote(long pid, void *remote_dst, const void *local_src, size_t bytes)
+{
+    if (!put((pid_t)(pid == (long)getpid() ? 0 : pid), remote_dst, local_src, bytes)) {
+        set_error(std::string("process_vm_writev into process ") + std::to_string(pid) + " failed (" + strerror(errno) + ")");
+        return ARCTE_E_ARG;
+    }
+    return ARCTE_OK;
+}
+
+void host_advise_huge(void *p, size_t bytes) { advise_huge(p, bytes); }
 
 }  // namespace arcte

@@ -9,9 +9,10 @@ grouped NCCL send/recv; each rank then assembles its own rows.  torch.distribute
 plumbing only: the process group tells the ranks apart, carries the 128-byte NCCL id once and a handful of
 integers per call.
 
-The rows come home through every rank's own PCIe link: rank 0 creates the result arrays in shared memory
-(/dev/shm), every rank streams its row block into its slice (csrc/hostcopy.cu), and rank 0 returns the
-matrix (the other ranks return None; ARCTE_CUDA_RESULT_ON_ALL_RANKS=1 maps it on every rank).
+The rows come home through every rank's own PCIe link: rank 0 allocates ordinary numpy arrays and every rank
+streams its row block straight into them (process_vm_writev from the pinned staging slots of csrc/hostcopy.cu);
+rank 0 returns the matrix, the other ranks None.  Where one process may not write into another, or every rank
+wants the matrix (ARCTE_CUDA_RESULT_ON_ALL_RANKS=1), the arrays live in /dev/shm and every rank maps them.
 """
 import os
 import sys
@@ -148,10 +149,42 @@ def ensure_communicator(eng):
     eng.comm_init(world, rank, uid)
 
 
+_remote_ok = {}   # world size -> bool: can every rank of this job write into rank 0's memory?
+
+
+def remote_writes_work(rank, world):
+    """One probe per job: every rank writes 8 bytes into a buffer of rank 0 with process_vm_writev (needs ptrace
+    permission on rank 0: same user and Yama scope <= 1, the usual case for the ranks of one torchrun)."""
+    from .engine import host_write_to
+    if os.environ.get("ARCTE_CUDA_NO_REMOTE_WRITES") == "1":
+        return False
+    key = world
+    if key not in _remote_ok:
+        probe = np.zeros(world, dtype=np.int64)
+        info = all_gather_int64([os.getpid(), probe.ctypes.data])
+        ok = 1
+        try:
+            host_write_to(int(info[0, 0]), int(info[0, 1]) + 8 * rank, np.array([rank + 1], dtype=np.int64))
+        except Exception:
+            ok = 0
+        _dist().barrier()
+        if rank == 0:
+            ok = int(ok and np.array_equal(probe, np.arange(1, world + 1)))
+        _remote_ok[key] = bool(all_gather_int64([ok])[:, 0].min())
+    return _remote_ok[key]
+
+
 def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_ranks=None):
     """One rank's share of arcte() inside a torch.distributed job.  Rank 0 returns the matrix, the other
-    ranks None (all_ranks / ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: everybody)."""
-    from .engine import get_engine
+    ranks None (all_ranks / ARCTE_CUDA_RESULT_ON_ALL_RANKS=1: everybody, through shared memory).
+
+    The rows come home through every rank's own PCIe link.  Default: rank 0 allocates ordinary numpy arrays
+    and every rank streams its row block straight into them (process_vm_writev from its pinned staging slots,
+    csrc/hostcopy.cu); the 1.0 values of a rank's rows are written the same way, never copied from the device.
+    Where writing into another process is not permitted, or every rank wants the matrix, the arrays live in
+    /dev/shm instead (SharedResult)."""
+    import scipy.sparse as sparse
+    from .engine import advise_huge, get_engine, host_write_to
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
     if world > 16:
@@ -171,7 +204,40 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
     n = eng.n
     eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
     nnz = eng.exchange_assemble()
-    # sizes of all blocks + a name for the shared arrays (rank 0 picks it)
+    structural = eng._values_structural
+    lo, hi = row_range(n, rank, world)
+    threads = max(2, (os.cpu_count() or 8) // world)
+
+    if not all_ranks and remote_writes_work(rank, world):
+        offsets = block_offsets(all_gather_int64([nnz])[:, 0])
+        total = int(offsets[-1])
+        addr = [0, 0, 0, 0]
+        if rank == 0:
+            indptr = np.empty(n + 1, dtype=np.int64)
+            indices = np.empty(max(total, 1), dtype=np.int32)
+            data = np.empty(max(total, 1), dtype=np.float64)
+            for a in (indices, data):
+                advise_huge(a)
+            addr = [os.getpid(), indptr.ctypes.data, indices.ctypes.data, data.ctypes.data]
+        pid, a_ptr, a_idx, a_dat = (int(x) for x in all_gather_int64(addr)[0])
+        o0 = int(offsets[rank])
+        ip = np.empty(hi - lo + 1, dtype=np.int64)
+        eng.fetch_block(ip, None, None)                       # this block's row pointers (small), made global below
+        eng.fetch_block_to(pid, 0, a_idx + 4 * o0, a_dat + 8 * o0, values_are_ones=structural, n_threads=threads)
+        host_write_to(pid, a_ptr + 8 * lo, ip + offsets[rank])   # neighbouring blocks write the same value at their common row
+        dist.barrier()
+        if rank != 0:
+            return None
+        if structural:
+            eng.patch_self_loops(data, indptr)                # rank 0 holds the same graph: all rows at once
+        indices, data = indices[:total], data[:total]
+        if max(2 * n, total) < 2 ** 31:
+            indptr = indptr.astype(np.int32)
+        else:
+            indices = indices.astype(np.int64)
+        return sparse.csr_matrix((data, indices, indptr), shape=(n, 2 * n), copy=False)
+
+    # ---- shared-memory variant ----
     tag_bits = uuid.uuid4().int & ((1 << 62) - 1) if rank == 0 else 0
     table = all_gather_int64([nnz, tag_bits])
     offsets = block_offsets(table[:, 0])
@@ -184,11 +250,9 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
     if rank != 0:
         res = SharedResult(tag, n, total, create=False)
     o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
-    lo, hi = row_range(n, rank, world)
     ip = np.empty(hi - lo + 1, dtype=np.int64)
     indices, data = np.asarray(res.arrays[1]), np.asarray(res.arrays[2])
-    structural = eng._values_structural
-    eng.fetch_block(ip, indices[o0:o1], data[o0:o1], values_are_ones=structural)
+    eng.fetch_block(ip, indices[o0:o1], data[o0:o1], values_are_ones=structural, n_threads=threads)
     if structural:
         eng.patch_self_loops(data[o0:o1], ip, lo, hi)
     place_block(res, rank, world, offsets, ip)

@@ -355,6 +355,14 @@ class Engine:
                                                 ptr(data) if self.out_nnz else None, int(bool(values_are_ones)),
                                                 int(n_threads)))
 
+    def fetch_block_to(self, pid, addr_indptr, addr_indices, addr_data, values_are_ones=False, n_threads=0):
+        """fetch_block with the destination arrays in another process: `pid` and three virtual addresses of that
+        process (0 = skip the array).  See arcte_cuda_fetch_features_to."""
+        check(self._L.arcte_cuda_fetch_features_to(self._h, int(pid), C.c_void_p(addr_indptr or None),
+                                                   C.c_void_p(addr_indices or None) if self.out_nnz else None,
+                                                   C.c_void_p(addr_data or None) if self.out_nnz else None,
+                                                   int(bool(values_are_ones)), int(n_threads)))
+
     def features(self):
         """The n x 2n CSR of arcte.py:683, index dtype chosen like scipy (int32 if it fits)."""
         nnz = self.out_nnz
@@ -546,6 +554,18 @@ def get_engine(device=0):
     if not e.auto_schedule and e.schedule != _SCHEDULES[name]:
         e.set_schedule(_SCHEDULES[name])
     return e
+
+
+def host_write_to(pid, address, array):
+    """Copy a contiguous numpy array to virtual address `address` of process `pid` (process_vm_writev)."""
+    a = np.ascontiguousarray(array)
+    check(_lib.load().arcte_cuda_host_write_to(int(pid), C.c_void_p(int(address)), ptr(a), a.nbytes))
+
+
+def advise_huge(array):
+    """Ask for huge pages for a (yet untouched) numpy array of this process."""
+    if array.nbytes:
+        check(_lib.load().arcte_cuda_host_advise_huge(ptr(array), array.nbytes))
 
 
 def device_count():
