@@ -50,10 +50,16 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
 
     if n_gpus == 1:
         eng = get_engine(0)
-        eng.set_graph(A, canonical=True)
-        eng.extract(rule, rho_eff, epsilon)
-        eng.assemble()
-        return eng.features()
+        t = [time.perf_counter()]
+        eng.set_graph(A, canonical=True); t.append(time.perf_counter())
+        eng.extract(rule, rho_eff, epsilon); t.append(time.perf_counter())
+        eng.assemble(); t.append(time.perf_counter())
+        X = eng.features(); t.append(time.perf_counter())
+        if os.environ.get("ARCTE_CUDA_DEBUG"):
+            import sys
+            print("[arcte] 1 GPU: set_graph %.1f ms, extract %.1f ms, assemble %.1f ms, features %.1f ms"
+                  % tuple(1e3 * (b - a) for a, b in zip(t[:-1], t[1:])), file=sys.stderr)
+        return X
 
     # single process, several GPUs: graph replicated, seeds dealt round-robin (arcte.py:651),
     # one host thread per GPU (ctypes drops the GIL).  After the walks every GPU pulls all

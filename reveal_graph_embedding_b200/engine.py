@@ -373,9 +373,16 @@ class Engine:
         data = np.empty(nnz, dtype=np.float64)
         # every stored value is 1.0 (arcte.py:379-381, :676-679) except the identity entry of a self-loop row:
         # unless the values were changed on the device they are written on the host, not copied
+        import os, sys, time
+        t0 = time.perf_counter()
         self.fetch_block(indptr, indices, data, values_are_ones=self._values_structural)
+        t1 = time.perf_counter()
         if self._values_structural:
             self.patch_self_loops(data, indptr)
+        if os.environ.get("ARCTE_CUDA_DEBUG"):
+            print("[arcte] features: fetch %.1f ms (%.2f GB indices%s), self-loop patch %.1f ms"
+                  % (1e3 * (t1 - t0), 4e-9 * nnz, " + %.2f GB of ones written" % (8e-9 * nnz) if self._values_structural else
+                     " + %.2f GB values" % (8e-9 * nnz), 1e3 * (time.perf_counter() - t1)), file=sys.stderr)
         if max(2 * self.n, nnz) < 2 ** 31:
             indptr = indptr.astype(np.int32)
         else:
@@ -416,9 +423,15 @@ class Engine:
         entry is 2.0) and the number of stored entries before it in the row."""
         if self._loops is None:
             ip, ix = self._indptr, self._indices
-            rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(ip))
-            k = np.flatnonzero(ix == rows) if ix.size else np.zeros(0, dtype=np.int64)
-            self._loops = (rows[k], k - ip[rows[k]])
+            # stored diagonal entries: scipy's C++ csr_diagonal on the pattern (no O(nnz) temporaries in numpy)
+            pattern = sparse.csr_matrix((np.ones(ix.size, dtype=np.int8), ix, ip), shape=(self.n, self.n), copy=False)
+            rows = np.flatnonzero(pattern.diagonal()).astype(np.int64)
+            # position of the diagonal inside each of those rows: only their entries are expanded
+            lens = (ip[rows + 1] - ip[rows]).astype(np.int64)
+            first = np.concatenate([[0], np.cumsum(lens)[:-1]]) if rows.size else np.zeros(0, dtype=np.int64)
+            within = np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(first, lens)
+            hit = ix[np.repeat(ip[rows], lens) + within] == np.repeat(rows, lens)
+            self._loops = (rows, within[hit])
         return self._loops
 
     def patch_self_loops(self, data, out_indptr, row_lo=0, row_hi=None):

@@ -41,6 +41,39 @@ class NodeIds(dict):
     def __iter__(self):
         return iter(range(self.array.size))
 
+    # every other dict read goes through the real dict, filled on first use (dict.get / copy / setdefault / pop
+    # bypass __getitem__, so they must see the entries: the reference returns a plain dict)
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def copy(self):
+        self._fill()
+        return dict(super().items())
+
+    def setdefault(self, k, default=None):
+        self._fill()
+        return super().setdefault(k, default)
+
+    def pop(self, *a):
+        self._fill()
+        return super().pop(*a)
+
+    def popitem(self):
+        self._fill()
+        return super().popitem()
+
+    def __setitem__(self, k, v):
+        self._fill()
+        super().__setitem__(k, v)
+
+    def __delitem__(self, k):
+        self._fill()
+        super().__delitem__(k)
+
+    def update(self, *a, **kw):
+        self._fill()
+        super().update(*a, **kw)
+
     def keys(self):
         self._fill()
         return super().keys()

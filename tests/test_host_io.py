@@ -180,3 +180,31 @@ def test_canonical_csr_host_logic():
     assert all(np.array_equal(a, b) for a, b in zip(before, (D.indices, D.data, D.indptr)))
     with pytest.raises(ValueError, match="square"):
         canonical_csr(sparse.csr_matrix((3, 4)))
+
+
+def test_node_ids_behaves_like_the_reference_dict():
+    """datarw.py:110-111 returns a plain dict; NodeIds must answer every dict read the same way."""
+    from reveal_graph_embedding_b200.io import NodeIds
+    d = NodeIds([20, 30, 40])
+    assert d[1] == 30 and d.get(1) == 30 and d.get(9) is None and d.get(9, -1) == -1
+    assert len(d) == 3 and 2 in d and 3 not in d and list(d) == [0, 1, 2]
+    assert d.copy() == {0: 20, 1: 30, 2: 40} and type(d.copy()) is dict
+    assert d.setdefault(0, 99) == 20 and dict(d.items()) == {0: 20, 1: 30, 2: 40}
+    assert d == {0: 20, 1: 30, 2: 40}
+
+
+def test_cli_undirected_flag_forms():
+    """`-u` alone, `-u true`, `-u False` (the reference's type=bool reads the last one as True)."""
+    import argparse
+    from reveal_graph_embedding_b200.entry_points import arcte as cli
+    parser = argparse.ArgumentParser()
+    for short, long_, dest, typ, default, required, text in cli._FLAGS:
+        if typ == "flag":
+            parser.add_argument(short, long_, dest=dest, nargs="?", const=True, default=default, type=cli._to_bool)
+        else:
+            parser.add_argument(short, long_, dest=dest, type=typ, default=default, required=required)
+    base = ["-i", "a", "-o", "b"]
+    assert parser.parse_args(base).undirected is False
+    assert parser.parse_args(base + ["-u"]).undirected is True
+    assert parser.parse_args(base + ["-u", "true"]).undirected is True
+    assert parser.parse_args(base + ["-u", "False"]).undirected is False
