@@ -196,14 +196,24 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
             local = torch.cuda.current_device()
         engine = get_engine(int(local))
     eng = engine
+    import time
+    dbg = os.environ.get("ARCTE_CUDA_DEBUG") and rank == 0
+    tm = [("start", time.perf_counter())]
+
+    def mark(name):
+        if dbg:
+            tm.append((name, time.perf_counter()))
     if upload:
         eng.set_graph(A, canonical=True)
     if all_ranks is None:
         all_ranks = result_on_all_ranks()
     ensure_communicator(eng)
+    mark("set_graph")
     n = eng.n
     eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
+    mark("extract")
     nnz = eng.exchange_assemble()
+    mark("exchange+assemble")
     structural = eng._values_structural
     lo, hi = row_range(n, rank, world)
     threads = max(2, (os.cpu_count() or 8) // world)
@@ -220,12 +230,15 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
                 advise_huge(a)
             addr = [os.getpid(), indptr.ctypes.data, indices.ctypes.data, data.ctypes.data]
         pid, a_ptr, a_idx, a_dat = (int(x) for x in all_gather_int64(addr)[0])
+        mark("sizes+alloc")
         o0 = int(offsets[rank])
         ip = np.empty(hi - lo + 1, dtype=np.int64)
         eng.fetch_block(ip, None, None)                       # this block's row pointers (small), made global below
         eng.fetch_block_to(pid, 0, a_idx + 4 * o0, a_dat + 8 * o0, values_are_ones=structural, n_threads=threads)
         host_write_to(pid, a_ptr + 8 * lo, ip + offsets[rank])   # neighbouring blocks write the same value at their common row
+        mark("own block home")
         dist.barrier()
+        mark("barrier (slowest rank)")
         if rank != 0:
             return None
         if structural:
@@ -235,7 +248,12 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
             indptr = indptr.astype(np.int32)
         else:
             indices = indices.astype(np.int64)
-        return sparse.csr_matrix((data, indices, indptr), shape=(n, 2 * n), copy=False)
+        X = sparse.csr_matrix((data, indices, indptr), shape=(n, 2 * n), copy=False)
+        mark("patch+csr")
+        if dbg:
+            print("[arcte] rank 0 of %d: " % world + ", ".join("%s %.1f ms" % (b[0], 1e3 * (b[1] - a[1])) for a, b in zip(tm[:-1], tm[1:])),
+                  file=sys.stderr)
+        return X
 
     # ---- shared-memory variant ----
     tag_bits = uuid.uuid4().int & ((1 << 62) - 1) if rank == 0 else 0
