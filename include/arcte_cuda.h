@@ -340,6 +340,13 @@ int arcte_cuda_fetch_features_to(arcte_cuda_ctx *ctx, int64_t pid, int64_t *dst_
 int arcte_cuda_host_write_to(int64_t pid, void *dst, const void *src, int64_t bytes);
 int arcte_cuda_host_advise_huge(void *p, int64_t bytes);
 
+/* A writable array of `count` doubles, all 1.0, that costs no fill: a 32 MB in-memory file of ones (created once
+   per process) mapped copy-on-write back to back over the whole range.  *mapped_bytes is what to hand to
+   arcte_cuda_host_ones_free.  The feature matrix's value array is built this way (every stored value is 1.0 except
+   self-loop diagonals, which the caller patches: those pages are copied on that write). */
+int arcte_cuda_host_ones_alloc(int64_t count, void **out, int64_t *mapped_bytes);
+int arcte_cuda_host_ones_free(void *p, int64_t mapped_bytes);
+
 /* -- page-locked host memory for results ------------------------------------- */
 /* cudaHostAlloc / cudaFreeHost: result buffers handed to arcte_cuda_get_features can be
    page-locked so the device-to-host copy runs at PCIe rate instead of through the

@@ -23,7 +23,7 @@ SYMBOLS = [
     "arcte_cuda_set_graph", "arcte_cuda_set_transition", "arcte_cuda_set_seeds", "arcte_cuda_build_transition", "arcte_cuda_get_transition",
     "arcte_cuda_get_seed_count", "arcte_cuda_get_seeds", "arcte_cuda_epsilon_effective",
     "arcte_cuda_push", "arcte_cuda_extract", "arcte_cuda_centrality", "arcte_cuda_get_segments",
-    "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features", "arcte_cuda_fetch_features", "arcte_cuda_fetch_features_to", "arcte_cuda_host_write_to", "arcte_cuda_host_advise_huge",
+    "arcte_cuda_segments_device", "arcte_cuda_export_segments", "arcte_cuda_assemble", "arcte_cuda_assemble_rows", "arcte_cuda_features_device", "arcte_cuda_get_features", "arcte_cuda_fetch_features", "arcte_cuda_fetch_features_to", "arcte_cuda_host_write_to", "arcte_cuda_host_advise_huge", "arcte_cuda_host_ones_alloc", "arcte_cuda_host_ones_free",
     "arcte_cuda_comm_unique_id", "arcte_cuda_comm_init", "arcte_cuda_comm_init_all", "arcte_cuda_comm_info", "arcte_cuda_exchange_assemble",
     "arcte_cuda_normalize_columns", "arcte_cuda_normalize_features", "arcte_cuda_chi2_contingency", "arcte_cuda_peak_snr",
     "arcte_cuda_chi2_psnr_weights", "arcte_cuda_community_weighting",
@@ -99,6 +99,8 @@ def load():
         L.arcte_cuda_fetch_features_to.argtypes = [vp, i64, vp, vp, vp, i32, i32]
         L.arcte_cuda_host_write_to.argtypes = [i64, vp, vp, i64]
         L.arcte_cuda_host_advise_huge.argtypes = [vp, i64]
+        L.arcte_cuda_host_ones_alloc.argtypes = [i64, C.POINTER(vp), C.POINTER(i64)]
+        L.arcte_cuda_host_ones_free.argtypes = [vp, i64]
         L.arcte_cuda_comm_unique_id.argtypes = [vp]
         L.arcte_cuda_comm_init.argtypes = [vp, i32, i32, vp]
         L.arcte_cuda_comm_init_all.argtypes = [vp, i32]

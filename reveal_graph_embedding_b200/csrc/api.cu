@@ -629,6 +629,21 @@ int arcte_cuda_host_advise_huge(void *p, int64_t bytes)
     return ARCTE_OK;
 }
 
+int arcte_cuda_host_ones_alloc(int64_t count, void **out, int64_t *mapped_bytes)
+{
+    if (!out || !mapped_bytes || count < 0) { set_error("host_ones_alloc: bad arguments"); return ARCTE_E_ARG; }
+    size_t mb = 0;
+    const int rc = host_ones_alloc((size_t)count, out, &mb);
+    *mapped_bytes = (int64_t)mb;
+    return rc;
+}
+
+int arcte_cuda_host_ones_free(void *p, int64_t mapped_bytes)
+{
+    host_ones_free(p, (size_t)(mapped_bytes > 0 ? mapped_bytes : 0));
+    return ARCTE_OK;
+}
+
 int arcte_cuda_host_alloc(void **out, int64_t bytes)
 {
     if (!out || bytes <= 0) { set_error("host_alloc: bad arguments"); return ARCTE_E_ARG; }

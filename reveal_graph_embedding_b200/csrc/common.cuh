@@ -109,6 +109,8 @@ int fetch_features(arcte_cuda_ctx *c, int64_t *host_indptr, int32_t *host_indice
                    int n_threads, long pid = 0);
 int host_write_remote(long pid, void *remote_dst, const void *local_src, size_t bytes);
 void host_advise_huge(void *p, size_t bytes);
+int host_ones_alloc(size_t count, void **out, size_t *mapped_bytes);
+void host_ones_free(void *p, size_t mapped_bytes);
 void free_ring(arcte_cuda_ctx *c);
 void comm_free(arcte_cuda_ctx *c);
 

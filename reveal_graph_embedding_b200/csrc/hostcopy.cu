@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -270,5 +271,63 @@ int host_write_remote(long pid, void *remote_dst, const void *local_src, size_t 
 }
 
 void host_advise_huge(void *p, size_t bytes) { advise_huge(p, bytes); }
+
+// ---- a value array of ones that costs no fill ------------------------------------------------------------
+// Every stored value of the feature matrix is 1.0 (arcte.py:379-381, :676-679) except a handful of 2.0 diagonals,
+// and writing 4 GB of ones into fresh pages was two thirds of the host side of a call.  Instead one 32 MB
+// in-memory file (memfd) is filled with 1.0 once per process and mapped MAP_PRIVATE over and over, back to back,
+// to cover the array: the pages are shared with the file until somebody writes to them (copy-on-write), so the
+// array is ordinary writable memory to the caller and costs a few hundred mmap calls to create.
+constexpr size_t kOnesTemplate = size_t(32) << 20;
+static int g_ones_fd = -1;
+static std::mutex g_ones_mutex;
+
+int host_ones_alloc(size_t count, void **out, size_t *mapped_bytes)
+{
+    *out = nullptr;
+    *mapped_bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_ones_mutex);
+        if (g_ones_fd < 0) {
+            const int fd = memfd_create("arcte_ones", MFD_CLOEXEC);
+            if (fd < 0 || ftruncate(fd, (off_t)kOnesTemplate) != 0) {
+                if (fd >= 0) close(fd);
+                set_error(std::string("ones template: memfd_create/ftruncate failed (") + strerror(errno) + ")");
+                return ARCTE_E_ARG;
+            }
+            void *t = mmap(nullptr, kOnesTemplate, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            if (t == MAP_FAILED) {
+                close(fd);
+                set_error(std::string("ones template: mmap failed (") + strerror(errno) + ")");
+                return ARCTE_E_ARG;
+            }
+            std::fill((double *)t, (double *)t + kOnesTemplate / sizeof(double), 1.0);
+            munmap(t, kOnesTemplate);
+            g_ones_fd = fd;
+        }
+    }
+    const size_t bytes = ((count * sizeof(double) + kOnesTemplate - 1) / kOnesTemplate) * kOnesTemplate;
+    if (bytes == 0) return ARCTE_OK;
+    char *base = (char *)mmap(nullptr, bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (base == MAP_FAILED) {
+        set_error(std::string("ones array: address range reservation failed (") + strerror(errno) + ")");
+        return ARCTE_E_NOMEM;
+    }
+    for (size_t off = 0; off < bytes; off += kOnesTemplate) {
+        if (mmap(base + off, kOnesTemplate, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_FIXED, g_ones_fd, 0) == MAP_FAILED) {
+            munmap(base, bytes);
+            set_error(std::string("ones array: mapping the template failed (") + strerror(errno) + ")");
+            return ARCTE_E_NOMEM;
+        }
+    }
+    *out = base;
+    *mapped_bytes = bytes;
+    return ARCTE_OK;
+}
+
+void host_ones_free(void *p, size_t mapped_bytes)
+{
+    if (p && mapped_bytes) munmap(p, mapped_bytes);
+}
 
 }  // namespace arcte

@@ -184,6 +184,7 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
     Where writing into another process is not permitted, or every rank wants the matrix, the arrays live in
     /dev/shm instead (SharedResult)."""
     import scipy.sparse as sparse
+    from . import hostmem
     from .engine import advise_huge, get_engine, host_write_to
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -225,16 +226,16 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
         if rank == 0:
             indptr = np.empty(n + 1, dtype=np.int64)
             indices = np.empty(max(total, 1), dtype=np.int32)
-            data = np.empty(max(total, 1), dtype=np.float64)
-            for a in (indices, data):
-                advise_huge(a)
+            advise_huge(indices)
+            # values: all ones but for the patched diagonals -> copy-on-write mappings of a block of ones
+            data = hostmem.ones(max(total, 1)) if structural else np.empty(max(total, 1), dtype=np.float64)
             addr = [os.getpid(), indptr.ctypes.data, indices.ctypes.data, data.ctypes.data]
         pid, a_ptr, a_idx, a_dat = (int(x) for x in all_gather_int64(addr)[0])
         mark("sizes+alloc")
         o0 = int(offsets[rank])
         ip = np.empty(hi - lo + 1, dtype=np.int64)
         eng.fetch_block(ip, None, None)                       # this block's row pointers (small), made global below
-        eng.fetch_block_to(pid, 0, a_idx + 4 * o0, a_dat + 8 * o0, values_are_ones=structural, n_threads=threads)
+        eng.fetch_block_to(pid, 0, a_idx + 4 * o0, 0 if structural else a_dat + 8 * o0, n_threads=threads)
         host_write_to(pid, a_ptr + 8 * lo, ip + offsets[rank])   # neighbouring blocks write the same value at their common row
         mark("own block home")
         dist.barrier()

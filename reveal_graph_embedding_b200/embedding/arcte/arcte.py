@@ -31,7 +31,7 @@ import time
 import numpy as np
 import scipy.sparse as sparse
 
-from ... import distributed
+from ... import distributed, hostmem
 from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, Engine, canonical_csr, device_count,
                        get_engine)
 
@@ -105,9 +105,9 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     total = int(offsets[-1])
     # plain numpy result arrays; every GPU streams its row block into its slice over its own PCIe link
     # (csrc/hostcopy.cu).  Every stored value is 1.0 except self-loop diagonals (arcte.py:379-381, :676-679):
-    # the values are written by the copy threads, not copied.
+    # the value array is copy-on-write mappings of a block of ones (hostmem.ones), neither copied nor written.
     indices = np.empty(total, dtype=np.int32)
-    data = np.empty(total, dtype=np.float64)
+    data = hostmem.ones(total)
     indptr = np.empty(n + 1, dtype=np.int64)
     threads_each = max(2, (os.cpu_count() or 8) // n_gpus)
 
@@ -115,7 +115,7 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
         lo, hi = distributed.row_range(n, rank, n_gpus)
         ip = np.empty(hi - lo + 1, dtype=np.int64)
         o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
-        engines[rank].fetch_block(ip, indices[o0:o1], data[o0:o1], values_are_ones=True, n_threads=threads_each)
+        engines[rank].fetch_block(ip, indices[o0:o1], None, n_threads=threads_each)
         engines[rank].patch_self_loops(data[o0:o1], ip, lo, hi)
         indptr[lo:hi + 1] = ip + offsets[rank]   # neighbouring blocks write the same value at their common row
 

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import scipy.sparse as sparse
 
-from . import _lib
+from . import _lib, hostmem
 from ._lib import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, SCHEDULE_FIFO, SCHEDULE_FRONTIER,  # noqa: F401
                    ArcteCudaError, check, ptr)
 
@@ -370,18 +370,23 @@ class Engine:
             raise ArcteCudaError("features(): only a row block is assembled; use the distributed path")
         indptr = np.empty(self.n + 1, dtype=np.int64)
         indices = np.empty(nnz, dtype=np.int32)
-        data = np.empty(nnz, dtype=np.float64)
         # every stored value is 1.0 (arcte.py:379-381, :676-679) except the identity entry of a self-loop row:
-        # unless the values were changed on the device they are written on the host, not copied
+        # unless the values were changed on the device they are neither copied nor written (hostmem.ones:
+        # copy-on-write mappings of a block of ones), only the 2.0 entries are patched in
         import os, sys, time
         t0 = time.perf_counter()
-        self.fetch_block(indptr, indices, data, values_are_ones=self._values_structural)
+        if self._values_structural:
+            data = hostmem.ones(nnz)
+            self.fetch_block(indptr, indices, None)
+        else:
+            data = np.empty(nnz, dtype=np.float64)
+            self.fetch_block(indptr, indices, data)
         t1 = time.perf_counter()
         if self._values_structural:
             self.patch_self_loops(data, indptr)
         if os.environ.get("ARCTE_CUDA_DEBUG"):
             print("[arcte] features: fetch %.1f ms (%.2f GB indices%s), self-loop patch %.1f ms"
-                  % (1e3 * (t1 - t0), 4e-9 * nnz, " + %.2f GB of ones written" % (8e-9 * nnz) if self._values_structural else
+                  % (1e3 * (t1 - t0), 4e-9 * nnz, " + %.2f GB of ones mapped" % (8e-9 * nnz) if self._values_structural else
                      " + %.2f GB values" % (8e-9 * nnz), 1e3 * (time.perf_counter() - t1)), file=sys.stderr)
         if max(2 * self.n, nnz) < 2 ** 31:
             indptr = indptr.astype(np.int32)
