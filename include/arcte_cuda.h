@@ -76,9 +76,13 @@ enum {
                                         accumulated in queue order by their first reference (shared memory);
                                         direct-mapped 32-byte {s, r, d_in, epoch} per node and walk: nothing is
                                         ever reset; 16 walks per SM                                          */
-    ARCTE_ENGINE_BATCHED_HASH = 2    /* the same batches, walk state in a growing open-addressing table of
+    ARCTE_ENGINE_BATCHED_HASH = 2,   /* the same batches, walk state in a growing open-addressing table of
                                         32-byte entries per walk (compact: the only engine whose memory does
                                         not grow with n per walk); experimental, slowest on the shapes measured */
+    ARCTE_ENGINE_FIFO_COMPACT = 3    /* one queue entry per warp iteration; the pairs of a walk live in first-touch
+                                        order in a compact array (first touches are coalesced writes, the threshold
+                                        sweep is sequential, nothing is ever reset), found through a 4-byte
+                                        epoch-tagged index map per node; all three rules                   */
 };
 
 /* Counters and device timings of the last arcte_cuda_extract/assemble on this context. */
@@ -131,7 +135,7 @@ int arcte_cuda_set_schedule(arcte_cuda_ctx *ctx, int schedule, int heavy_permill
 /* Selects the engine of the FIFO schedule (ARCTE_ENGINE_*); table_capacity > 0 bounds the entries of one
    walk's hash table half (rounded up to a power of two; a walk that outgrows it is re-run by
    ARCTE_ENGINE_FIFO_DENSE), 0 = as many as 2n or the memory budget allows.  The environment variable
-   ARCTE_CUDA_ENGINE=fifo|dense|hash overrides AUTO. */
+   ARCTE_CUDA_ENGINE=fifo|dense|hash|compact overrides AUTO. */
 int arcte_cuda_set_engine(arcte_cuda_ctx *ctx, int engine, int64_t table_capacity);
 
 /* -- a11 + a1: graph upload and transition build --------------------------- */

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("ARCTE_CUDA_LIB") or os.path.join(_HERE, "libarcte_cud
 
 RULE_ABSORBING, RULE_PAGERANK, RULE_LAZY = 0, 1, 2
 SCHEDULE_FIFO, SCHEDULE_FRONTIER = 0, 1
-ENGINE_AUTO, ENGINE_FIFO_DENSE, ENGINE_BATCHED_DENSE, ENGINE_BATCHED_HASH = -1, 0, 1, 2
+ENGINE_AUTO, ENGINE_FIFO_DENSE, ENGINE_BATCHED_DENSE, ENGINE_BATCHED_HASH, ENGINE_FIFO_COMPACT = -1, 0, 1, 2, 3
 
 # every symbol include/arcte_cuda.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [

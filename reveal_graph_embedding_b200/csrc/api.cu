@@ -147,6 +147,13 @@ int arcte_cuda_create(arcte_cuda_ctx **out, int device_id)
             fprintf(stderr, "[arcte] L2 %d MB, persisting max %d MB (set %zu MB), window max %d MB\n", prop.l2CacheSize >> 20,
                     prop.persistingL2CacheMaxSize >> 20, c->l2_persist_bytes >> 20, prop.accessPolicyMaxWindowSize >> 20);
     }
+    {   // Experiment switch: ARCTE_CUDA_L2_FETCH=32|64|128 sets the L2 fetch granularity (bytes DRAM delivers per missing sector)
+        const char *env = getenv("ARCTE_CUDA_L2_FETCH");
+        size_t cur = 0;
+        if (env && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atol(env)) != cudaSuccess) (void)cudaGetLastError();
+        if (getenv("ARCTE_CUDA_DEBUG") && cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity) == cudaSuccess)
+            fprintf(stderr, "[arcte] L2 fetch granularity %zu bytes\n", cur);
+    }
     *out = c;
     return ARCTE_OK;
 }
@@ -158,7 +165,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->graph_arena, &c->indptr, &c->indices, &c->adj, &c->w, &c->d_out, &c->d_in, &c->colcnt, &c->node_info, &c->edge_wd, &c->edge_din, &c->seeds,
                       &c->work_seed, &c->work_eps, &c->seg_count, &c->seg_offset, &c->members, &c->retry_list,
-                      &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->slots.frontier, &c->slots.fval, &c->counters, &c->out_indptr,
+                      &c->slots.sr, &c->slots.touched, &c->slots.queue, &c->slots.cmap, &c->slots.cepoch, &c->slots.frontier, &c->slots.fval, &c->counters, &c->out_indptr,
                       &c->out_indices, &c->out_data};
     for (DevBuf *b : bufs) dev_free(*b);
     for (DevBuf &b : c->scratch) dev_free(b);
@@ -166,7 +173,8 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
                        &c->fo_indptr[0], &c->fo_indptr[1], &c->fo_indices[0], &c->fo_indices[1], &c->fo_data[0], &c->fo_data[1]};
     for (DevBuf *b : fbufs) dev_free(*b);
     for (DevBuf &b : c->peer_stage) dev_free(b);
-    DevBuf *pbufs[] = {&c->bpool.tbl, &c->bpool.stage, &c->bpool.clean, &c->bpool.queue, &c->row_w};
+    DevBuf *pbufs[] = {&c->bpool.tbl, &c->bpool.stage, &c->bpool.clean, &c->bpool.queue, &c->row_w, &c->to_walk, &c->from_walk,
+                       &c->walk_info, &c->walk_row_w, &c->walk_indices, &c->work_seed_w};
     for (DevBuf *b : pbufs) dev_free(*b);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -224,7 +232,7 @@ int arcte_cuda_set_schedule(arcte_cuda_ctx *c, int schedule, int heavy_permille,
 int arcte_cuda_set_engine(arcte_cuda_ctx *c, int engine, int64_t table_capacity)
 {
     CHECK_CTX(c);
-    if (engine < ARCTE_ENGINE_AUTO || engine > ARCTE_ENGINE_BATCHED_HASH || table_capacity < 0 ||
+    if (engine < ARCTE_ENGINE_AUTO || engine > ARCTE_ENGINE_FIFO_COMPACT || table_capacity < 0 ||
         table_capacity > (int64_t(1) << 26)) {
         set_error("set_engine: argument out of range");
         return ARCTE_E_ARG;
@@ -252,11 +260,14 @@ static int upload_structure(arcte_cuda_ctx *c, int64_t n, int64_t nnz, const int
     }
     c->have_graph = c->have_transition = c->have_segments = c->have_features = false;
     c->row_w_valid = false;
+    c->walk_labels_valid = false;
     if (n != c->n) {
         // slot geometry depends on n: drop the pool (re-created lazily)
         dev_free(c->slots.sr);
         dev_free(c->slots.touched);
         dev_free(c->slots.queue);
+        dev_free(c->slots.cmap);
+        dev_free(c->slots.cepoch);
         dev_free(c->slots.frontier);
         dev_free(c->slots.fval);
         c->slots = SlotPool();

@@ -63,7 +63,12 @@ struct __align__(16) NodeInfo {
 struct SlotPool {
     DevBuf sr;       // double2 [n_slots][n]
     DevBuf touched;  // int32   [n_slots][n]
-    DevBuf queue;    // int32   [n_slots][queue_cap]
+    DevBuf queue;    // int32   [n_slots][queue_cap]  (compact engine: int2 {node, compact index})
+    DevBuf cmap;     // uint32  [n_slots][map_stride]  compact engine: epoch-tagged index map
+    DevBuf cepoch;   // uint32  [n_slots]              compact engine: epoch of the last walk of each slot
+    bool compact = false;     // sr holds compact pairs (not the all-zero dense arrays the dense FIFO engine relies on)
+    int64_t map_stride = 0;
+    int64_t ccap = 0;         // compact engine: pairs / touched entries per slot (dense engines: n)
     DevBuf frontier; // int32   [frontier_slots][2][n]  (frontier schedule only)
     DevBuf fval;     // double  [frontier_slots][n]     (frontier schedule only)
     int64_t frontier_slots = 0;
@@ -180,6 +185,13 @@ struct arcte_cuda_ctx {
     arcte::BatchedPool bpool;
     arcte::DevBuf row_w;       // double [n]  the repeated transition weight of each row (uniform_rows)
     bool row_w_valid = false, uniform_rows = false;
+    // walk labels (transition.cu, K2c): the label space the FIFO-schedule push kernels run in
+    arcte::DevBuf to_walk, from_walk;     // int32 [n]  node -> walk label and back
+    arcte::DevBuf walk_info;              // NodeInfo [n]  node records by walk label
+    arcte::DevBuf walk_row_w;             // double [n]
+    arcte::DevBuf walk_indices;           // int32 [nnz]  column indices in walk labels, rows where and as they were
+    arcte::DevBuf work_seed_w;            // int32 [S]  the shard's seeds in walk labels
+    bool walk_labels_valid = false;
     arcte::DevBuf counters;  // int64 [PC_COUNT]
 
     // assembly output

@@ -189,6 +189,139 @@ __device__ __forceinline__ bool push_node(const PushParams &P, double2 *__restri
 #endif
 constexpr int kEpiUnroll = ARCTE_EPI_UNROLL;  // touched entries per lane in flight in the threshold sweep
 
+// K4 of one finished walk: threshold, membership, sparse reset of the slot and the per-warp totals.
+template <int RULE>
+__device__ __forceinline__ void threshold_and_emit(const PushParams &P, double2 *__restrict__ sr,
+                                                   int32_t *__restrict__ touched, const Walk &wk,
+                                                   unsigned long long *ws, unsigned long long *wtot, int pos, int seed,
+                                                   int lane, unsigned lt)
+{
+    // ---------------- K4: threshold + membership (arcte.py:352-376) ----------------
+    const NodeInfo si = P.info[seed];
+    const int base_size = (int)si.len + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
+    bool emit = true;
+    if (RULE != ARCTE_RULE_ABSORBING) {
+        // arcte.py:129-133 / :241-245: intersect1d(base, support).size >= base.size
+        int inside = 0;
+        for (unsigned j = lane; j < si.len; j += 32) {
+            const int v = P.indices[si.begin + j];
+            inside += (v != seed && ld_state(&sr[v]).x != 0.0);
+        }
+        inside = warp_sum_i(inside) + (ld_state(&sr[seed]).x != 0.0 ? 1 : 0);
+        emit = inside >= base_size;
+    }
+    double tau_v = 0.0;
+    if (emit) {
+        double q = __ddiv_rn(ld_state(&sr[seed]).x, si.d_in);
+        for (unsigned j0 = 0; j0 < si.len; j0 += 64) {
+            int v[2];
+            double2 o[2];
+            double d[2];
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const unsigned j = j0 + k2 * 32 + lane;
+                v[k2] = j < si.len ? P.indices[si.begin + j] : -1;
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2)
+                if (v[k2] >= 0) {
+                    o[k2] = ld_state(&sr[v[k2]]);
+                    d[k2] = ld_info_din(&P.info[v[k2]]);
+                }
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2)
+                if (v[k2] >= 0) q = fmin(q, __ddiv_rn(o[k2].x, d[k2]));  // arcte.py:355-356
+        }
+        tau_v = warp_min(q);  // arcte.py:359-360
+    }
+    const Threshold tau = make_threshold(tau_v);
+    // One sweep over the touched list: count the support, keep (compacted in place, in
+    // list order) the nodes with s/d_in >= tau -- arcte.py:363-367, searchsorted 'left' --
+    // and zero the state (the sparse form of s[:]=0; r[:]=0, arcte.py:337-338).
+    int m = 0, support = 0;
+    for (int i0 = 0; i0 < wk.nt; i0 += 32 * kEpiUnroll) {
+        int x[kEpiUnroll];
+        double sx[kEpiUnroll], dx[kEpiUnroll];
+#pragma unroll
+        for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+            const int i = i0 + k2 * 32 + lane;
+            x[k2] = i < wk.nt ? touched[i] : -1;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+            if (x[k2] >= 0) {
+                sx[k2] = ld_state(&sr[x[k2]]).x;
+                dx[k2] = ld_info_din(&P.info[x[k2]]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
+            if (i0 + k2 * 32 >= wk.nt) break;  // warp-uniform
+            bool in_sup = false, pass = false;
+            if (x[k2] >= 0) {
+                st_state(&sr[x[k2]], make_double2(0.0, 0.0));
+                in_sup = sx[k2] != 0.0;
+                pass = emit && in_sup && quot_ge(sx[k2], dx[k2], tau);
+                // arcte.pyx:164-191: centrality += s / d_in over the support of every seed, in 2^-38 fixed
+                // point so that the sum does not depend on the order the seeds finish in
+                if (P.centrality && in_sup)
+                    atomicAdd(&P.centrality[P.from_walk ? P.from_walk[x[k2]] : x[k2]], __double2ull_rn(__dmul_rn(__ddiv_rn(sx[k2], dx[k2]), P.cent_scale)));
+            }
+            support += __popc(__ballot_sync(kFull, in_sup));
+            if (emit) {
+                const unsigned mp = __ballot_sync(kFull, pass);
+                if (pass) touched[m + __popc(mp & lt)] = x[k2];
+                m += __popc(mp);
+            }
+        }
+    }
+    __syncwarp();
+    emit = emit && (m > base_size);  // arcte.py:370
+    bool write = false;
+    if (emit) {
+        int64_t off;
+        if (P.retry_pass && P.seg_count[pos] > 0) {
+            off = P.seg_offset[pos];  // offset was assigned in the pass that overflowed
+        } else {
+            unsigned long long o = 0;
+            if (lane == 0) o = atomicAdd(&P.counters[PC_MEMBER_CURSOR], (unsigned long long)m);
+            off = (int64_t)__shfl_sync(kFull, o, 0);
+        }
+        write = off + m <= P.member_cap;
+        if (write)
+            for (int i = lane; i < m; i += 32)
+                P.members[off + i] = P.from_walk ? P.from_walk[touched[i]] : touched[i];  // arcte.py:372-376
+        if (lane == 0) {
+            P.seg_count[pos] = m;
+            P.seg_offset[pos] = off;
+            if (!write) {
+                const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
+                P.retry_list[r] = pos;
+            }
+        }
+    } else if (lane == 0) {
+        P.seg_count[pos] = 0;
+        P.seg_offset[pos] = 0;
+    }
+    __syncwarp();
+
+    if (lane == 0 && (!emit || write)) {  // a seed whose members did not fit is re-run and counted then
+        wtot[WS_PUSHES] += ws[WS_PUSHES];
+        wtot[WS_EDGES] += ws[WS_EDGES];
+        wtot[WS_ENQ] += ws[WS_ENQ];
+        if (ws[WS_MAXQ] > wtot[WS_MAXQ]) wtot[WS_MAXQ] = ws[WS_MAXQ];
+        wtot[WS_SUPPORT] += support;
+        wtot[WS_TOUCHED] += wk.nt;
+        wtot[WS_SEEDDEG] += si.len;
+        if (emit) {
+            wtot[WS_MEMBERS] += m;
+            wtot[WS_EMITTED] += 1;
+        }
+    }
+    __syncwarp();
+}
+
 #ifndef ARCTE_PUSH_MIN_BLOCKS
 #define ARCTE_PUSH_MIN_BLOCKS 4
 #endif
@@ -291,129 +424,7 @@ k_push_threshold(const PushParams P)
             continue;
         }
 
-        // ---------------- K4: threshold + membership (arcte.py:352-376) ----------------
-        const NodeInfo si = P.info[seed];
-        const int base_size = (int)si.len + 1;  // np.append(adjacent_nodes[n], n), arcte.py:358
-        bool emit = true;
-        if (RULE != ARCTE_RULE_ABSORBING) {
-            // arcte.py:129-133 / :241-245: intersect1d(base, support).size >= base.size
-            int inside = 0;
-            for (unsigned j = lane; j < si.len; j += 32) {
-                const int v = P.indices[si.begin + j];
-                inside += (v != seed && ld_state(&sr[v]).x != 0.0);
-            }
-            inside = warp_sum_i(inside) + (ld_state(&sr[seed]).x != 0.0 ? 1 : 0);
-            emit = inside >= base_size;
-        }
-        double tau_v = 0.0;
-        if (emit) {
-            double q = __ddiv_rn(ld_state(&sr[seed]).x, si.d_in);
-            for (unsigned j0 = 0; j0 < si.len; j0 += 64) {
-                int v[2];
-                double2 o[2];
-                double d[2];
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                    const unsigned j = j0 + k2 * 32 + lane;
-                    v[k2] = j < si.len ? P.indices[si.begin + j] : -1;
-                }
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2)
-                    if (v[k2] >= 0) {
-                        o[k2] = ld_state(&sr[v[k2]]);
-                        d[k2] = ld_info_din(&P.info[v[k2]]);
-                    }
-#pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2)
-                    if (v[k2] >= 0) q = fmin(q, __ddiv_rn(o[k2].x, d[k2]));  // arcte.py:355-356
-            }
-            tau_v = warp_min(q);  // arcte.py:359-360
-        }
-        const Threshold tau = make_threshold(tau_v);
-        // One sweep over the touched list: count the support, keep (compacted in place, in
-        // list order) the nodes with s/d_in >= tau -- arcte.py:363-367, searchsorted 'left' --
-        // and zero the state (the sparse form of s[:]=0; r[:]=0, arcte.py:337-338).
-        int m = 0, support = 0;
-        for (int i0 = 0; i0 < wk.nt; i0 += 32 * kEpiUnroll) {
-            int x[kEpiUnroll];
-            double sx[kEpiUnroll], dx[kEpiUnroll];
-#pragma unroll
-            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
-                const int i = i0 + k2 * 32 + lane;
-                x[k2] = i < wk.nt ? touched[i] : -1;
-            }
-#pragma unroll
-            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
-                if (x[k2] >= 0) {
-                    sx[k2] = ld_state(&sr[x[k2]]).x;
-                    dx[k2] = ld_info_din(&P.info[x[k2]]);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k2 = 0; k2 < kEpiUnroll; ++k2) {
-                if (i0 + k2 * 32 >= wk.nt) break;  // warp-uniform
-                bool in_sup = false, pass = false;
-                if (x[k2] >= 0) {
-                    st_state(&sr[x[k2]], make_double2(0.0, 0.0));
-                    in_sup = sx[k2] != 0.0;
-                    pass = emit && in_sup && quot_ge(sx[k2], dx[k2], tau);
-                    // arcte.pyx:164-191: centrality += s / d_in over the support of every seed, in 2^-38 fixed
-                    // point so that the sum does not depend on the order the seeds finish in
-                    if (P.centrality && in_sup)
-                        atomicAdd(&P.centrality[x[k2]], __double2ull_rn(__dmul_rn(__ddiv_rn(sx[k2], dx[k2]), P.cent_scale)));
-                }
-                support += __popc(__ballot_sync(kFull, in_sup));
-                if (emit) {
-                    const unsigned mp = __ballot_sync(kFull, pass);
-                    if (pass) touched[m + __popc(mp & lt)] = x[k2];
-                    m += __popc(mp);
-                }
-            }
-        }
-        __syncwarp();
-        emit = emit && (m > base_size);  // arcte.py:370
-        bool write = false;
-        if (emit) {
-            int64_t off;
-            if (P.retry_pass && P.seg_count[pos] > 0) {
-                off = P.seg_offset[pos];  // offset was assigned in the pass that overflowed
-            } else {
-                unsigned long long o = 0;
-                if (lane == 0) o = atomicAdd(&P.counters[PC_MEMBER_CURSOR], (unsigned long long)m);
-                off = (int64_t)__shfl_sync(kFull, o, 0);
-            }
-            write = off + m <= P.member_cap;
-            if (write)
-                for (int i = lane; i < m; i += 32) P.members[off + i] = touched[i];  // arcte.py:372-376
-            if (lane == 0) {
-                P.seg_count[pos] = m;
-                P.seg_offset[pos] = off;
-                if (!write) {
-                    const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
-                    P.retry_list[r] = pos;
-                }
-            }
-        } else if (lane == 0) {
-            P.seg_count[pos] = 0;
-            P.seg_offset[pos] = 0;
-        }
-        __syncwarp();
-
-        if (lane == 0 && (!emit || write)) {  // a seed whose members did not fit is re-run and counted then
-            wtot[WS_PUSHES] += ws[WS_PUSHES];
-            wtot[WS_EDGES] += ws[WS_EDGES];
-            wtot[WS_ENQ] += ws[WS_ENQ];
-            if (ws[WS_MAXQ] > wtot[WS_MAXQ]) wtot[WS_MAXQ] = ws[WS_MAXQ];
-            wtot[WS_SUPPORT] += support;
-            wtot[WS_TOUCHED] += wk.nt;
-            wtot[WS_SEEDDEG] += si.len;
-            if (emit) {
-                wtot[WS_MEMBERS] += m;
-                wtot[WS_EMITTED] += 1;
-            }
-        }
-        __syncwarp();
+        threshold_and_emit<RULE>(P, sr, touched, wk, ws, wtot, pos, seed, lane, lt);
     }
 
     if (lane == 0 && !P.debug_keep) {
@@ -435,12 +446,336 @@ k_push_threshold(const PushParams P)
     }
 }
 
+// ---- the pipelined walk loop ----------------------------------------------------------------------------
+// Same queue discipline, same arithmetic, same results as k_push_threshold; what changes is WHEN the loads are
+// issued.  One pop of the loop above is a chain of four dependent round trips -- ring entry, {node record, state
+// pair}, the row, the neighbours' state pairs -- and with the ~7 neighbours of a typical pushed node a warp has a
+// handful of sectors in flight at any time: the launch ran at the LATENCY of that chain (about 6,300 cycles per
+// push, profiles/r2_pipelined_fifo.md), not at any throughput limit.  Here
+//   * the next 32 ring entries and their node records sit in a shared-memory window per warp (one coalesced ring
+//     read and one record gather per 32 pops; their state pairs and rows are prefetched into L2 on the way);
+//   * while the neighbours of pop k are being gathered, the state pair of pop k+1 and the first 32 entries of its
+//     row are already on their way (speculatively: a pop that fails the threshold wastes the row read);
+//   * a pair that was loaded early is patched in registers when push k rewrites it (pop k+1 a neighbour of
+//     pop k, or the same node again), so the value tested is exactly the one the reference tests;
+//   * inside a long row the next 32 column indices and weights are loaded before the current ones are consumed.
+// Per push the chain is one gather deep.
+#ifndef ARCTE_PIPE_MIN_BLOCKS
+#define ARCTE_PIPE_MIN_BLOCKS 3
+#endif
+constexpr int kPipeWarps = 8;   // warps per CTA
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+struct PipeWindow {
+    int32_t u[kPipeWarps][32];
+    NodeInfo info[kPipeWarps][32];
+};
+
+template <int RULE>
+__device__ __forceinline__ bool push_node_pipe(const PushParams &P, double2 *__restrict__ sr,
+                                               int32_t *__restrict__ touched, int32_t *__restrict__ queue, Walk &wk,
+                                               unsigned long long *ws, int u, double2 su, unsigned begin, unsigned len,
+                                               const Threshold *eps_sh, int lane, unsigned lt, bool pre, int pv, double pw,
+                                               int nu, double2 *patch, bool &patched)
+{
+    double c;
+    double2 su_new;
+    if (RULE == ARCTE_RULE_ABSORBING) {
+        c = __dmul_rn(P.one_minus_rho, su.y);                       // push.py:57
+        su_new = make_double2(su.x, 0.0);                           // push.py:60
+    } else {
+        const double a = __dmul_rn(P.rho, su.y);                    // push.py:9
+        c = __dmul_rn(P.one_minus_rho, su.y);                       // push.py:10
+        su_new = make_double2(__dadd_rn(su.x, a), 0.0);             // push.py:13-14
+    }
+    // The pair of the next pop is in flight (loaded early): nothing here may wait for it, so a value this push
+    // gives it goes to `patch` (shared memory) and replaces the loaded one when the pop is taken.
+    if (lane == 0) {
+        st_state(&sr[u], su_new);
+        ws[WS_PUSHES] += 1;
+        ws[WS_EDGES] += len;
+        if (nu == u) *patch = su_new;   // the same node is popped again next
+    }
+    patched = nu == u;
+    __syncwarp();
+    const unsigned qmask = (unsigned)P.queue_cap - 1u;
+    const int32_t *__restrict__ idx = P.indices + begin;
+    const double *__restrict__ wgt = P.w + begin;
+    int v = -1;
+    double wv = 0.0;
+    if (pre) {
+        v = pv;
+        wv = pw;
+    } else if ((unsigned)lane < len) {
+        v = ld_index(idx + lane);
+        wv = ld_weight(wgt + lane);
+    }
+    for (unsigned base = 0; base < len; base += 32) {
+        // the neighbours' state pairs and in-degrees: independent gathers, all in flight
+        double2 o = make_double2(0.0, 0.0);
+        double dv = 1.0;
+        if (v >= 0) {
+            o = ld_state(&sr[v]);
+            dv = ld_info_din(&P.info[v]);
+        }
+        // the next 32 entries of a long row, before the gathers are consumed
+        int v2 = -1;
+        double wv2 = 0.0;
+        const unsigned j2 = base + 32 + lane;
+        if (j2 < len) {
+            v2 = ld_index(idx + j2);
+            wv2 = ld_weight(wgt + j2);
+        }
+        bool is_new = false, enq = false;
+        double2 nw = o;
+        if (v >= 0) {
+            const double p = __dmul_rn(c, wv);
+            if (RULE == ARCTE_RULE_ABSORBING) nw.x = __dadd_rn(o.x, p);   // push.py:63
+            nw.y = __dadd_rn(o.y, p);                                     // push.py:64 / :17
+            st_state(&sr[v], nw);
+            is_new = (o.x == 0.0 && o.y == 0.0) && (nw.x != 0.0 || nw.y != 0.0);
+            enq = quot_ge(nw.y, dv, *eps_sh);                             // similarity.py:194 / :214
+        }
+        if (nu >= 0) {   // the pair that was loaded early is rewritten by this push: take the value just stored
+            const unsigned hit = __ballot_sync(kFull, v == nu);
+            if (v == nu) *patch = nw;
+            patched = patched || hit != 0u;
+        }
+        // ordered appends (CSR order = lane order).  Every node touched above is recorded BEFORE the ring can
+        // report overflow, so an aborted walk can always be undone through the touched list.
+        const unsigned m_new = __ballot_sync(kFull, is_new);
+        if (is_new) touched[wk.nt + __popc(m_new & lt)] = v;
+        wk.nt += __popc(m_new);
+        const unsigned m_enq = __ballot_sync(kFull, enq);
+        const unsigned cnt = __popc(m_enq);
+        if (cnt) {
+            if (wk.tail - wk.head + cnt > (unsigned)P.queue_cap) return false;
+            if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = v;
+            wk.tail += cnt;
+            if (lane == 0) ws[WS_ENQ] += cnt;
+        }
+        v = v2;
+        wv = wv2;
+    }
+    if (lane == 0 && wk.tail - wk.head > ws[WS_MAXQ]) ws[WS_MAXQ] = wk.tail - wk.head;
+    __syncwarp();
+    return true;
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(32 * kPipeWarps, ARCTE_PIPE_MIN_BLOCKS)
+k_push_pipelined(const PushParams P)
+{
+    __shared__ unsigned long long wstat[kPipeWarps][2][WS_COUNT];
+    __shared__ PipeWindow win;
+    __shared__ double2 patch_buf[kPipeWarps];
+    __shared__ Threshold eps_buf[kPipeWarps];   // walk-constant, read where it is used: registers are for the loads in flight
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const int wid = threadIdx.x >> 5;
+    const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= P.n_slots) return;
+    double2 *__restrict__ sr = P.sr + slot * P.n;
+    int32_t *__restrict__ touched = P.touched + slot * P.n;
+    int32_t *__restrict__ queue = P.queue + slot * P.queue_cap;
+    const unsigned qmask = (unsigned)P.queue_cap - 1u;
+    unsigned long long *wtot = wstat[wid][0];
+    unsigned long long *ws = wstat[wid][1];
+    int32_t *win_u = win.u[wid];
+    NodeInfo *win_i = win.info[wid];
+    if (lane < WS_COUNT) wtot[lane] = 0ull;
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long t_begin;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+        wtot[WS_T_BEGIN] = t_begin;
+    }
+
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&P.counters[PC_WORK_CURSOR], 1ull);
+        k = __shfl_sync(kFull, k, 0);
+        if ((int64_t)k >= P.n_work) break;
+        const int pos = P.work_ids ? P.work_ids[k] : (int)k;
+        const int seed = P.work_seed[pos];
+        if (lane == 0) eps_buf[wid] = make_threshold(P.work_eps[pos]);
+        const Threshold *eps_sh = &eps_buf[wid];
+
+        Walk wk;
+        wk.head = wk.tail = 0;
+        wk.nt = 1;
+        if (lane < WS_COUNT) ws[lane] = 0ull;
+        double2 su = make_double2(RULE == ARCTE_RULE_ABSORBING ? 1.0 : 0.0, 1.0);   // similarity.py:176-177 / :26
+        if (lane == 0) {
+            st_state(&sr[seed], su);
+            touched[0] = seed;
+        }
+        __syncwarp();
+
+        int u = seed;
+        unsigned u_begin, u_len;
+        double u_din;
+        {
+            const NodeInfo iu = ld_info(&P.info[seed]);
+            u_begin = iu.begin;
+            u_len = iu.len;
+            u_din = iu.d_in;
+        }
+        bool first = true, ok = true, pre = false;
+        int pv = -1;
+        double pw = 0.0;
+        unsigned wbase = 0, wn = 0;   // the window holds ring positions [wbase, wbase + wn)
+        // Ring positions [pos, min(pos + 32, tail)) -> window: ids, node records; their state pairs and rows -> L2.
+        auto refill = [&](unsigned at) {
+            __syncwarp();
+            wbase = at;
+            wn = min(32u, wk.tail - at);
+            if ((unsigned)lane < wn) {
+                const int x = queue[(at + lane) & qmask];
+                const NodeInfo ix = ld_info(&P.info[x]);
+                prefetch_l2(&sr[x]);
+                win_u[lane] = x;
+                win_i[lane] = ix;
+                prefetch_l2(P.indices + ix.begin);
+                prefetch_l2(P.w + ix.begin);
+            }
+            __syncwarp();
+        };
+        for (;;) {
+            const bool do_push = first || quot_ge(su.y, u_din, *eps_sh);   // similarity.py:183 / :204
+            const bool have_next = wk.head != wk.tail;
+            int nu = -1, nv = -1;
+            double2 nsu = su;
+            double nwt = 0.0;
+            if (have_next) {
+                if (wk.head - wbase >= wn) refill(wk.head);
+                nu = win_u[wk.head - wbase];
+                nsu = ld_state(&sr[nu]);
+                const NodeInfo ni = win_i[wk.head - wbase];
+                if ((unsigned)lane < ni.len) {
+                    nv = ld_index(P.indices + ni.begin + lane);
+                    nwt = ld_weight(P.w + ni.begin + lane);
+                }
+            }
+            bool patched = false;
+            if (do_push) {
+                ok = push_node_pipe<RULE>(P, sr, touched, queue, wk, ws, u, su, u_begin, u_len, eps_sh, lane, lt, pre, pv,
+                                          pw, nu, &patch_buf[wid], patched);
+                if (!ok) break;
+            }
+            if (patched) nsu = patch_buf[wid];   // (push_node_pipe ends with __syncwarp)
+            first = false;
+            bool npre = have_next;
+            if (!have_next) {
+                if (wk.head == wk.tail) break;
+                refill(wk.head);   // the ring was empty before this push: nothing could be fetched ahead
+                nu = win_u[0];
+                nsu = ld_state(&sr[nu]);
+                npre = false;
+            }
+            {   // the record of the pop being taken: from the window, not from registers held across the push
+                const NodeInfo ni = win_i[wk.head - wbase];
+                u_begin = ni.begin;
+                u_len = ni.len;
+                u_din = ni.d_in;
+            }
+            wk.head += 1;
+            u = nu;
+            su = nsu;
+            pre = npre;
+            pv = nv;
+            pw = nwt;
+        }
+
+        if (P.debug_keep) {
+            if (lane == 0) {
+                P.counters[PC_PUSHES] = ws[WS_PUSHES];
+                P.counters[PC_TOUCHED] = (unsigned long long)wk.nt;
+                P.counters[PC_OVERFLOW_SEEDS] = ok ? 0ull : 1ull;
+            }
+            return;
+        }
+        if (!ok) {
+            // FIFO ring too small: undo and hand the seed to the retry pass
+            __syncwarp();
+            for (int i = lane; i < wk.nt; i += 32) st_state(&sr[touched[i]], make_double2(0.0, 0.0));
+            if (lane == 0) {
+                const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
+                P.retry_list[r] = pos;
+                atomicAdd(&P.counters[PC_QOVERFLOW], 1ull);
+                P.seg_count[pos] = -1;
+            }
+            __syncwarp();
+            continue;
+        }
+        threshold_and_emit<RULE>(P, sr, touched, wk, ws, wtot, pos, seed, lane, lt);
+    }
+
+    if (lane == 0 && !P.debug_keep) {
+        atomicAdd(&P.counters[PC_PUSHES], wtot[WS_PUSHES]);
+        atomicAdd(&P.counters[PC_EDGES], wtot[WS_EDGES]);
+        atomicAdd(&P.counters[PC_ENQUEUES], wtot[WS_ENQ]);
+        atomicMax(&P.counters[PC_MAXQ], wtot[WS_MAXQ]);
+        atomicAdd(&P.counters[PC_SUPPORT], wtot[WS_SUPPORT]);
+        atomicAdd(&P.counters[PC_TOUCHED], wtot[WS_TOUCHED]);
+        atomicAdd(&P.counters[PC_SEEDDEG], wtot[WS_SEEDDEG]);
+        atomicAdd(&P.counters[PC_MEMBERS], wtot[WS_MEMBERS]);
+        atomicAdd(&P.counters[PC_EMITTED], wtot[WS_EMITTED]);
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        atomicMin(&P.counters[PC_T_START], wtot[WS_T_BEGIN]);
+        atomicMax(&P.counters[PC_T_END], t_end);
+        atomicAdd(&P.counters[PC_T_BUSY], t_end - wtot[WS_T_BEGIN]);
+    }
+}
+
 // ---- small helper kernels ---------------------------------------------------------------
 __global__ void k_build_work(int64_t n_work, int shard_rank, int shard_count,
                              const int32_t *__restrict__ seeds, int32_t *__restrict__ work_seed)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_work) work_seed[i] = seeds[shard_rank + i * shard_count];  // arcte.py:19-23
+}
+
+__global__ void k_to_walk_labels(int64_t n_work, const int32_t *__restrict__ work_seed, const int32_t *__restrict__ to_walk,
+                                 int32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_work) out[i] = to_walk[work_seed[i]];
+}
+
+// The graph as the FIFO-schedule kernels see it: in walk labels when they were built (transition.cu, K2c).
+static void fill_graph_params(const arcte_cuda_ctx *c, PushParams &P, bool walk_labels)
+{
+    P.info = walk_labels ? c->walk_info.as<NodeInfo>() : c->node_info.as<NodeInfo>();
+    P.indices = walk_labels ? c->walk_indices.as<int32_t>() : c->indices.as<int32_t>();
+    P.row_w = walk_labels ? c->walk_row_w.as<double>() : c->row_w.as<double>();
+    P.from_walk = walk_labels ? c->from_walk.as<int32_t>() : nullptr;
+}
+
+constexpr int kCompactWarpsPerSm = 40;   // 5 CTAs of 8 warps at 48 registers (push_compact.cu: ARCTE_COMPACT_MIN_BLOCKS)
+
+static int bits_for(int64_t v)   // bits needed for values 0 .. v-1 (at least 1)
+{
+    int b = 1;
+    while ((int64_t(1) << b) < v) ++b;
+    return b;
+}
+
+static void fill_compact_params(const arcte_cuda_ctx *c, PushParams &P)
+{
+    P.cmap = c->slots.cmap.as<uint32_t>();
+    P.cepoch = c->slots.cepoch.as<uint32_t>();
+    P.map_stride = c->slots.map_stride;
+    P.idx_bits = bits_for(c->n);
+    P.ccap = c->slots.ccap;
+    P.sr = c->slots.sr.as<double2>();
+    P.touched = c->slots.touched.as<int32_t>();
+    P.queue = c->slots.queue.as<int32_t>();
+    P.queue_cap = c->slots.queue_cap;
+    const char *env = getenv("ARCTE_CUDA_COMPACT_EPOCH_BITS");   // tests: force the epoch field to wrap early
+    if (env && atoi(env) >= 2 && 32 - atoi(env) >= P.idx_bits) P.idx_bits = 32 - atoi(env);
 }
 
 __global__ void k_gather_eps(int64_t n_work, int shard_rank, int shard_count,
@@ -452,19 +787,21 @@ __global__ void k_gather_eps(int64_t n_work, int shard_rank, int shard_count,
 
 __global__ void k_split_and_reset(int64_t n, int64_t n_touched, double2 *__restrict__ sr,
                                   const int32_t *__restrict__ touched, double *__restrict__ s_out,
-                                  double *__restrict__ r_out, int phase, double inv_scale)
+                                  double *__restrict__ r_out, int phase, double inv_scale,
+                                  const int32_t *__restrict__ from_walk)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (phase == 0) {
         if (i < n) {
+            const int64_t o = from_walk ? from_walk[i] : i;
             if (inv_scale == 0.0) {
                 const double2 v = sr[i];
-                s_out[i] = v.x;
-                r_out[i] = v.y;
+                s_out[o] = v.x;
+                r_out[o] = v.y;
             } else {  // frontier schedule: unsigned 64-bit fixed point
                 const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(sr)[i];
-                s_out[i] = __dmul_rn(__ull2double_rn(v.x), inv_scale);
-                r_out[i] = __dmul_rn(__ull2double_rn(v.y), inv_scale);
+                s_out[o] = __dmul_rn(__ull2double_rn(v.x), inv_scale);
+                r_out[o] = __dmul_rn(__ull2double_rn(v.y), inv_scale);
             }
         }
     } else if (i < n_touched) {
@@ -477,27 +814,42 @@ static inline unsigned grid_for(int64_t items, int block) { return (unsigned)((i
 int compute_eps_effective(arcte_cuda_ctx *c, double epsilon, const int32_t *dev_seeds,
                           int64_t n_seeds, double *dev_eps_out);
 
-// Allocate (or re-shape) the slot pool.  States are zeroed once here and every seed
-// leaves its slot all-zero again, so the pool is reused across extractions as is.
-static int ensure_slots(arcte_cuda_ctx *c, int64_t want_slots, int64_t queue_cap)
+// Allocate (or re-shape) the slot pool.  Dense engine: states are zeroed once here and every seed leaves its slot
+// all-zero again, so the pool is reused across extractions as is.  Compact engine (push_compact.cu): `sr` holds the
+// pairs by compact index and is never cleared; the index map starts all-zero with epoch 0 and the FIFO rings hold
+// 8-byte entries.
+static int ensure_slots(arcte_cuda_ctx *c, int64_t want_slots, int64_t queue_cap, bool compact, int64_t ccap = 0)
 {
     SlotPool &sp = c->slots;
-    const bool same_state = (sp.n == c->n && sp.n_slots >= want_slots);
+    if (!compact || ccap <= 0 || ccap > c->n) ccap = c->n;
+    const bool same_state = (sp.n == c->n && sp.n_slots >= want_slots && sp.compact == compact && sp.ccap == ccap);
+    const size_t qe = compact ? sizeof(int2) : sizeof(int32_t);
     if (!same_state) {
         dev_free(sp.sr);
         dev_free(sp.touched);
         dev_free(sp.queue);
+        dev_free(sp.cmap);
+        dev_free(sp.cepoch);
         sp.n_slots = sp.queue_slots = 0;
-        ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)want_slots * (size_t)c->n));
-        ARCTE_TRY(dev_reserve(sp.touched, sizeof(int32_t) * (size_t)want_slots * (size_t)c->n));
-        ARCTE_CUDA_TRY(cudaMemsetAsync(sp.sr.p, 0, sizeof(double2) * (size_t)want_slots * (size_t)c->n,
-                                       c->stream));
+        ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)want_slots * (size_t)ccap));
+        ARCTE_TRY(dev_reserve(sp.touched, sizeof(int32_t) * (size_t)want_slots * (size_t)ccap));
+        sp.ccap = ccap;
+        if (compact) {
+            sp.map_stride = (c->n + 3) / 4 * 4;
+            ARCTE_TRY(dev_reserve(sp.cmap, sizeof(uint32_t) * (size_t)want_slots * (size_t)sp.map_stride));
+            ARCTE_TRY(dev_reserve(sp.cepoch, sizeof(uint32_t) * (size_t)want_slots));
+            ARCTE_CUDA_TRY(cudaMemsetAsync(sp.cmap.p, 0, sizeof(uint32_t) * (size_t)want_slots * (size_t)sp.map_stride, c->stream));
+            ARCTE_CUDA_TRY(cudaMemsetAsync(sp.cepoch.p, 0, sizeof(uint32_t) * (size_t)want_slots, c->stream));
+        } else {
+            ARCTE_CUDA_TRY(cudaMemsetAsync(sp.sr.p, 0, sizeof(double2) * (size_t)want_slots * (size_t)c->n, c->stream));
+        }
         sp.n = c->n;
         sp.n_slots = want_slots;
+        sp.compact = compact;
     }
     if (sp.queue_cap != queue_cap || sp.queue_slots < want_slots) {
         dev_free(sp.queue);
-        ARCTE_TRY(dev_reserve(sp.queue, sizeof(int32_t) * (size_t)sp.n_slots * (size_t)queue_cap));
+        ARCTE_TRY(dev_reserve(sp.queue, qe * (size_t)sp.n_slots * (size_t)queue_cap));
         sp.queue_cap = queue_cap;
         sp.queue_slots = sp.n_slots;
     }
@@ -522,10 +874,18 @@ static void fill_rule_constants(PushParams &P, double rho)
 
 static int launch_push(arcte_cuda_ctx *c, int rule, const PushParams &P)
 {
+    if (P.cmap) return compact_launch(c, rule, P);
     const unsigned grid = grid_for(P.n_slots * 32, 256);
+    static const bool pipelined = !(getenv("ARCTE_CUDA_PIPELINED") && !strcmp(getenv("ARCTE_CUDA_PIPELINED"), "0"));
     switch (rule) {
-    case ARCTE_RULE_ABSORBING: k_push_threshold<ARCTE_RULE_ABSORBING><<<grid, 256, 0, c->stream>>>(P); break;
-    case ARCTE_RULE_PAGERANK: k_push_threshold<ARCTE_RULE_PAGERANK><<<grid, 256, 0, c->stream>>>(P); break;
+    case ARCTE_RULE_ABSORBING:
+        if (pipelined) k_push_pipelined<ARCTE_RULE_ABSORBING><<<grid, 32 * kPipeWarps, 0, c->stream>>>(P);
+        else k_push_threshold<ARCTE_RULE_ABSORBING><<<grid, 256, 0, c->stream>>>(P);
+        break;
+    case ARCTE_RULE_PAGERANK:
+        if (pipelined) k_push_pipelined<ARCTE_RULE_PAGERANK><<<grid, 32 * kPipeWarps, 0, c->stream>>>(P);
+        else k_push_threshold<ARCTE_RULE_PAGERANK><<<grid, 256, 0, c->stream>>>(P);
+        break;
     case ARCTE_RULE_LAZY: k_push_threshold<ARCTE_RULE_LAZY><<<grid, 256, 0, c->stream>>>(P); break;
     default: set_error("unknown push rule"); return ARCTE_E_ARG;
     }
@@ -535,9 +895,22 @@ static int launch_push(arcte_cuda_ctx *c, int rule, const PushParams &P)
 }
 
 // Slot-pool geometry for this graph: how many walks can be in flight.
-static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap)
+// Compact engine: pairs per slot.  The supports of the bench shapes stay below 10^5 nodes (the reference scales
+// epsilon with the seed's degree, arcte.py:26-50), so a quarter of a million pairs per walk is plenty; the rare walk
+// that needs more is re-run with room for all n nodes (extract_shard's retry pass).
+static int64_t compact_cap(const arcte_cuda_ctx *c, bool full)
 {
-    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : 32;
+    int64_t cap = int64_t(1) << 18;
+    const char *env = getenv("ARCTE_CUDA_COMPACT_CAP");
+    if (env && atoll(env) > 0) cap = atoll(env);
+    return (full || cap > c->n) ? c->n : cap;
+}
+
+static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap, bool compact,
+                      bool full_cap = false)
+{
+    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? kCompactWarpsPerSm : 32);
+    const int64_t ccap = compact ? compact_cap(c, full_cap) : c->n;
     int64_t want = (int64_t)c->sm_count * wps;
     want = ((want + 7) / 8) * 8;
     int64_t qcap = c->queue_cap_cfg > 0 ? c->queue_cap_cfg : (c->n < 65536 ? c->n : 65536);
@@ -548,17 +921,17 @@ static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64
     if (want < 8) want = 8;
     // keep whatever is already allocated if it is big enough (avoids re-zeroing)
     if (c->slots.n == c->n && c->slots.n_slots >= want && c->slots.queue_slots >= want &&
-        c->slots.queue_cap == qcap) {
+        c->slots.queue_cap == qcap && c->slots.compact == compact && c->slots.ccap == ccap) {
         *n_slots = want;
         *queue_cap = qcap;
         return ARCTE_OK;
     }
     size_t free_b = 0, total_b = 0;
     ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes;
+    free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes + c->slots.cmap.bytes;
     const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
     const double budget = (double)free_b * pct / 100.0;
-    const double per_slot = 16.0 * c->n + 4.0 * c->n + 4.0 * qcap;
+    const double per_slot = 20.0 * ccap + (compact ? 4.0 * c->n + 8.0 * qcap : 4.0 * qcap);
     int64_t fit = (int64_t)(budget / per_slot);
     fit = (fit / 8) * 8;
     if (fit < 8) {
@@ -580,6 +953,8 @@ static void release_other_pools(arcte_cuda_ctx *c, bool batched, int engine)
         dev_free(c->slots.sr);
         dev_free(c->slots.touched);
         dev_free(c->slots.queue);
+        dev_free(c->slots.cmap);
+        dev_free(c->slots.cepoch);
         dev_free(c->slots.frontier);
         dev_free(c->slots.fval);
         c->slots = SlotPool();
@@ -595,13 +970,18 @@ static void release_other_pools(arcte_cuda_ctx *c, bool batched, int engine)
 // Which engine of the FIFO schedule walks this call (include/arcte_cuda.h, ARCTE_ENGINE_*).
 static int resolve_engine(const arcte_cuda_ctx *c, int rule)
 {
-    if (rule != ARCTE_RULE_ABSORBING) return ARCTE_ENGINE_FIFO_DENSE;
     int e = c->engine;
+    if (rule != ARCTE_RULE_ABSORBING) {   // the batched engines implement the absorbing rule only
+        const char *env = getenv("ARCTE_CUDA_ENGINE");
+        if (e == ARCTE_ENGINE_AUTO && env && !strcmp(env, "compact")) e = ARCTE_ENGINE_FIFO_COMPACT;
+        return e == ARCTE_ENGINE_FIFO_COMPACT ? e : ARCTE_ENGINE_FIFO_DENSE;
+    }
     if (e == ARCTE_ENGINE_AUTO) {
         const char *env = getenv("ARCTE_CUDA_ENGINE");
         if (env && !strcmp(env, "fifo")) e = ARCTE_ENGINE_FIFO_DENSE;
         else if (env && !strcmp(env, "dense")) e = ARCTE_ENGINE_BATCHED_DENSE;
         else if (env && !strcmp(env, "hash")) e = ARCTE_ENGINE_BATCHED_HASH;
+        else if (env && !strcmp(env, "compact")) e = ARCTE_ENGINE_FIFO_COMPACT;
     }
     // measured (profiles/r2_engines.md): the batched direct-mapped engine wins on medium graphs (Flickr shape 134
     // vs 166 ms, BA(150000,3) 14.6 vs 19.7 ms); tiny graphs and the 1.1 M-node bench shape go to the FIFO engine
@@ -669,12 +1049,15 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         return ARCTE_E_ARG;
     }
     int64_t n_slots = 0, qcap = 0;
-    const int engine = (frontier || c->centrality_acc) ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
-    const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
+    int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
+    if (c->centrality_acc && engine != ARCTE_ENGINE_FIFO_COMPACT) engine = ARCTE_ENGINE_FIFO_DENSE;
+    const bool compact = engine == ARCTE_ENGINE_FIFO_COMPACT;
+    const bool batched = !frontier && !compact && engine != ARCTE_ENGINE_FIFO_DENSE;
     if (c->centrality_acc && (frontier || rule != ARCTE_RULE_ABSORBING)) {
         set_error("centrality: absorbing rule, FIFO schedule only");
         return ARCTE_E_ARG;
     }
+    const bool walk_labels = c->walk_labels_valid && !frontier;   // the frontier schedule keeps the caller's labels
     release_other_pools(c, batched, engine);
     if (frontier) {
         ARCTE_TRY(frontier_plan_slots(c, S, &n_slots));
@@ -683,8 +1066,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         ARCTE_TRY(batched_plan(c, engine, S, &n_slots, &qcap));
         ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
     } else {
-        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap));
-        ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap, compact));
+        ARCTE_TRY(ensure_slots(c, n_slots, qcap, compact, compact_cap(c, false)));
     }
     stt.engine = frontier ? -2 : engine;
     if (c->member_cap == 0) {
@@ -704,14 +1087,18 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
 
     PushParams P{};
     P.n = c->n;
-    P.info = c->node_info.as<NodeInfo>();
-    P.indices = c->indices.as<int32_t>();
     P.w = c->w.as<double>();
     P.wd = c->edge_wd.as<double2>();
     P.edge_din = c->edge_din.as<double>();
     P.uniform_rows = c->uniform_rows ? 1 : 0;
-    P.row_w = c->row_w.as<double>();
     P.work_seed = c->work_seed.as<int32_t>();
+    if (walk_labels) {
+        ARCTE_TRY(dev_reserve(c->work_seed_w, sizeof(int32_t) * S1));
+        k_to_walk_labels<<<grid_for(S, 256), 256, 0, st>>>(S, c->work_seed.as<int32_t>(), c->to_walk.as<int32_t>(),
+                                                           c->work_seed_w.as<int32_t>());
+        ++stt.launches;
+        P.work_seed = c->work_seed_w.as<int32_t>();
+    }
     P.work_eps = c->work_eps.as<double>();
     P.work_ids = nullptr;
     P.n_work = S;
@@ -735,6 +1122,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.inv_scale = 1.0 / P.scale;
     }
     if (batched) batched_fill_params(c, engine, P);
+    fill_graph_params(c, P, walk_labels);
+    if (compact) fill_compact_params(c, P);
     P.centrality = c->centrality_acc;
     P.cent_scale = 274877906944.0;   // 2^38
 
@@ -769,12 +1158,19 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         const int64_t n_retry = hc[PC_OVERFLOW_SEEDS];
         stt.retries += n_retry;
         if (++rounds > 12) { set_error("extract: retry passes did not converge"); return ARCTE_E_OVERFLOW; }
+        if (compact && hc[PC_TOVERFLOW] > 0 && c->slots.ccap < c->n) {
+            // walks that touched more nodes than a slot has pairs: fewer slots with room for all n nodes
+            int64_t ls = 0, lq = 0;
+            ARCTE_TRY(plan_slots(c, n_retry, &ls, &lq, true, true));
+            ARCTE_TRY(ensure_slots(c, ls, lq, true, c->n));
+            fill_compact_params(c, P);
+        }
         if (batched && rounds == 1) {
             // seeds the batched engine gave up on (ring, table region or member range too small) are re-run
             // by the dense FIFO engine: same results, and its rings grow as far as memory allows
             int64_t ls = 0, lq = 0;
-            ARCTE_TRY(plan_slots(c, n_retry, &ls, &lq));
-            ARCTE_TRY(ensure_slots(c, ls, lq));
+            ARCTE_TRY(plan_slots(c, n_retry, &ls, &lq, false));
+            ARCTE_TRY(ensure_slots(c, ls, lq, false));
             P.sr = c->slots.sr.as<double2>();
             P.touched = c->slots.touched.as<int32_t>();
             P.queue = c->slots.queue.as<int32_t>();
@@ -804,13 +1200,14 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
             size_t free_b = 0, total_b = 0;
             ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
             free_b += c->slots.queue.bytes;
-            while (r_slots > 8 && (double)r_slots * r_qcap * 4.0 > 0.8 * (double)free_b) r_slots -= 8;
-            if ((double)r_slots * r_qcap * 4.0 > 0.8 * (double)free_b) {
+            const double qe = compact ? 8.0 : 4.0;   // bytes per ring entry
+            while (r_slots > 8 && (double)r_slots * r_qcap * qe > 0.8 * (double)free_b) r_slots -= 8;
+            if ((double)r_slots * r_qcap * qe > 0.8 * (double)free_b) {
                 set_error("extract: FIFO ring cannot be grown further (out of device memory)");
                 return ARCTE_E_OVERFLOW;
             }
             dev_free(c->slots.queue);
-            ARCTE_TRY(dev_reserve(c->slots.queue, sizeof(int32_t) * (size_t)r_slots * (size_t)r_qcap));
+            ARCTE_TRY(dev_reserve(c->slots.queue, (size_t)qe * (size_t)r_slots * (size_t)r_qcap));
             c->slots.queue_cap = r_qcap;
             c->slots.queue_slots = r_slots;  // fewer, larger rings until the next plan_slots
         }
@@ -882,20 +1279,26 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         return ARCTE_E_ARG;
     }
     int engine = frontier ? ARCTE_ENGINE_FIFO_DENSE : resolve_engine(c, rule);
+    const bool compact = engine == ARCTE_ENGINE_FIFO_COMPACT;
     ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
     ARCTE_TRY(dev_reserve(c->scratch[0], sizeof(int32_t) * 4));
     ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(double) * 4));
     ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(double) * 2 * (size_t)c->n));
     const int32_t seed32 = (int32_t)seed;
+    const bool walk_labels = c->walk_labels_valid && !frontier;
     ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[0].p, &seed32, sizeof(seed32), cudaMemcpyHostToDevice, st));
+    if (walk_labels) {
+        k_to_walk_labels<<<1, 32, 0, st>>>(1, c->scratch[0].as<int32_t>(), c->to_walk.as<int32_t>(), c->scratch[0].as<int32_t>() + 1);
+        ++c->stats.launches;
+    }
     ARCTE_CUDA_TRY(cudaMemcpyAsync(c->scratch[2].p, &eps_eff, sizeof(eps_eff), cudaMemcpyHostToDevice, st));
     double *s_dev = c->scratch[3].as<double>();
     double *r_dev = s_dev + c->n;
 
     int64_t cap = 0;
-    bool pools_ready = false;
+    bool pools_ready = false, full_cap = false;
     for (int attempt = 0;; ++attempt) {
-        const bool batched = !frontier && engine != ARCTE_ENGINE_FIFO_DENSE;
+        const bool batched = !frontier && !compact && engine != ARCTE_ENGINE_FIFO_DENSE;
         if (!pools_ready) {
             int64_t n_slots = 0, qcap = 0;
             if (attempt == 0) release_other_pools(c, batched, engine);
@@ -906,8 +1309,8 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
                 ARCTE_TRY(batched_plan(c, engine, 1, &n_slots, &qcap));
                 ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
             } else {
-                ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap));
-                ARCTE_TRY(ensure_slots(c, n_slots, qcap));
+                ARCTE_TRY(plan_slots(c, 1, &n_slots, &qcap, compact, full_cap));
+                ARCTE_TRY(ensure_slots(c, n_slots, qcap, compact, compact_cap(c, full_cap)));
             }
             cap = c->slots.queue_cap;
             pools_ready = true;
@@ -915,14 +1318,11 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         ARCTE_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(int64_t) * PC_COUNT, st));
         PushParams P{};
         P.n = c->n;
-        P.info = c->node_info.as<NodeInfo>();
-        P.indices = c->indices.as<int32_t>();
         P.w = c->w.as<double>();
         P.wd = c->edge_wd.as<double2>();
         P.edge_din = c->edge_din.as<double>();
         P.uniform_rows = c->uniform_rows ? 1 : 0;
-        P.row_w = c->row_w.as<double>();
-        P.work_seed = c->scratch[0].as<int32_t>();
+        P.work_seed = c->scratch[0].as<int32_t>() + (walk_labels ? 1 : 0);
         P.work_eps = c->scratch[2].as<double>();
         P.n_work = 1;
         P.sr = c->slots.sr.as<double2>();
@@ -933,6 +1333,8 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         P.counters = c->counters.as<unsigned long long>();
         P.debug_keep = 1;
         fill_rule_constants(P, rho);
+        fill_graph_params(c, P, walk_labels);
+        if (compact) fill_compact_params(c, P);
         double inv_scale = 0.0;
         const bool hash = batched;   // both batched engines write the dense vectors themselves and clean up
         if (frontier) {
@@ -942,6 +1344,7 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
             ARCTE_TRY(frontier_launch(c, P, 1, false));
         } else if (batched) {
             batched_fill_params(c, engine, P);
+            fill_graph_params(c, P, walk_labels);
             P.dbg_s = s_dev;
             P.dbg_r = r_dev;
             if (hash) ARCTE_CUDA_TRY(cudaMemsetAsync(s_dev, 0, sizeof(double) * 2 * (size_t)c->n, st));
@@ -954,21 +1357,28 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
         const int64_t nt = hc[PC_TOUCHED];
         if (hc[PC_OVERFLOW_SEEDS] == 0) {
-            if (!hash) {
-                k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0, inv_scale);
+            if (compact) {
+                ARCTE_TRY(compact_scatter(c, P, nt, s_dev, r_dev));
+            } else if (!hash) {
+                k_split_and_reset<<<grid_for(c->n, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 0, inv_scale, P.from_walk);
                 ++c->stats.launches;
             }
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_s, s_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
             ARCTE_CUDA_TRY(cudaMemcpyAsync(host_r, r_dev, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, st));
         }
-        if (nt > 0 && !hash) {   // the hash engine leaves its table empty itself
-            k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1, inv_scale);
+        if (nt > 0 && !hash && !compact) {   // the hash engine leaves its table empty itself, the compact one needs no reset
+            k_split_and_reset<<<grid_for(nt, 256), 256, 0, st>>>(c->n, nt, P.sr, P.touched, s_dev, r_dev, 1, inv_scale, P.from_walk);
             ++c->stats.launches;
         }
         ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
         if (hc[PC_OVERFLOW_SEEDS] == 0) {
             if (n_push) *n_push = hc[PC_PUSHES];
             return ARCTE_OK;
+        }
+        if (compact && hc[PC_TOVERFLOW] > 0 && !full_cap) {   // more touched nodes than a slot has pairs
+            full_cap = true;
+            pools_ready = false;
+            continue;
         }
         if (batched) {   // ring or table region too small: the dense FIFO engine takes the seed (its ring grows below)
             engine = ARCTE_ENGINE_FIFO_DENSE;
@@ -981,10 +1391,10 @@ int push_single(arcte_cuda_ctx *c, int rule, int64_t seed, double rho, double ep
             set_error("push: FIFO ring cannot be grown further for this seed");
             return ARCTE_E_OVERFLOW;
         }
-        if ((size_t)next * sizeof(int32_t) > c->slots.queue.bytes) {
+        if ((size_t)next * (compact ? sizeof(int2) : sizeof(int32_t)) > c->slots.queue.bytes) {
             dev_free(c->slots.queue);
             c->slots.queue_slots = 0;
-            ARCTE_TRY(dev_reserve(c->slots.queue, sizeof(int32_t) * (size_t)next));
+            ARCTE_TRY(dev_reserve(c->slots.queue, (compact ? sizeof(int2) : sizeof(int32_t)) * (size_t)next));
             c->slots.queue_cap = next;
             c->slots.queue_slots = 1;  // the next plan_slots re-creates the per-slot rings
         }

@@ -70,6 +70,13 @@ struct PushParams {
     const double *edge_din;    // [nnz] in-degree of the target of every stored entry
     int uniform_rows;          // 1: every row of w holds one repeated value, kept in row_w
     const double *row_w;       // [n] that value (uniform_rows)
+    const int32_t *from_walk;  // [n] walk label -> node id for everything that leaves the kernel, or nullptr (labels are node ids)
+    // compact-state FIFO engine (push_compact.cu): `sr` holds the pairs by compact index, `queue` holds int2 {node, index}
+    uint32_t *cmap;            // [n_slots][map_stride] (epoch << idx_bits) | compact index of the node in the walk of that epoch
+    uint32_t *cepoch;          // [n_slots] epoch of the last walk of the slot
+    int64_t map_stride;        // entries per slot in cmap (n rounded up to a multiple of 4)
+    int idx_bits;              // bits of the compact index in a map entry
+    int64_t ccap;              // pairs (and touched entries) per slot: a walk that touches more nodes is re-run with ccap = n
 };
 
 
@@ -78,6 +85,10 @@ int batched_plan(arcte_cuda_ctx *c, int engine, int64_t n_work, int64_t *n_slots
 int batched_ensure(arcte_cuda_ctx *c, int engine, int64_t n_slots, int64_t queue_cap);
 void batched_fill_params(arcte_cuda_ctx *c, int engine, PushParams &P);
 int batched_launch(arcte_cuda_ctx *c, int engine, const PushParams &P);
+
+// Implemented in push_compact.cu.
+int compact_launch(arcte_cuda_ctx *c, int rule, const PushParams &P);
+int compact_scatter(arcte_cuda_ctx *c, const PushParams &P, int64_t nt, double *s_dev, double *r_dev);
 
 // Implemented in push_frontier.cu.
 int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots);

@@ -872,8 +872,9 @@ k_walk_batched(const PushParams P)
                     const TableEntry e = ld_entry(S.T + i);
                     if (e.key != kEmptyKey) {
                         if (result == WALK_OK) {
-                            P.dbg_s[e.key] = e.s;
-                            P.dbg_r[e.key] = e.r;
+                            const int o = P.from_walk ? P.from_walk[e.key] : e.key;
+                            P.dbg_s[o] = e.s;
+                            P.dbg_r[o] = e.r;
                         }
                         S.T[i].key = kEmptyKey;
                     }
@@ -883,8 +884,9 @@ k_walk_batched(const PushParams P)
                 for (int i = lane; i < S.nt; i += 32) {
                     const int x = S.touched[i];
                     const TableEntry e = ld_entry(S.T + x);
-                    P.dbg_s[x] = e.s;
-                    P.dbg_r[x] = e.r;
+                    const int o = P.from_walk ? P.from_walk[x] : x;
+                    P.dbg_s[o] = e.s;
+                    P.dbg_r[o] = e.r;
                 }
             }
             if (lane == 0) {
@@ -1022,7 +1024,8 @@ k_walk_batched(const PushParams P)
             }
             write = off + m <= P.member_cap;
             if (write)
-                for (int i = lane; i < m; i += 32) P.members[off + i] = S.touched[i];   // arcte.py:372-376
+                for (int i = lane; i < m; i += 32)
+                    P.members[off + i] = P.from_walk ? P.from_walk[S.touched[i]] : S.touched[i];   // arcte.py:372-376
             if (lane == 0) {
                 P.seg_count[pos] = m;
                 P.seg_offset[pos] = off;

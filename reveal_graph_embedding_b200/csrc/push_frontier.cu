@@ -492,14 +492,14 @@ int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots)
     int64_t want = (int64_t)c->sm_count * (g.heavy_ctas > g.light_ctas ? g.heavy_ctas : g.light_ctas);
     if (want > n_work) want = n_work;
     if (want < 1) want = 1;
-    if (c->slots.n == c->n && c->slots.n_slots >= want && c->slots.frontier_slots >= want) {
+    if (c->slots.n == c->n && c->slots.n_slots >= want && c->slots.frontier_slots >= want && !c->slots.compact) {
         *n_slots = want;
         return ARCTE_OK;
     }
     size_t free_b = 0, total_b = 0;
     ARCTE_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     free_b += c->slots.sr.bytes + c->slots.touched.bytes + c->slots.queue.bytes + c->slots.frontier.bytes +
-              c->slots.fval.bytes;
+              c->slots.fval.bytes + c->slots.cmap.bytes;
     const int pct = c->mem_percent > 0 ? c->mem_percent : 60;
     const double per_slot = 36.0 * (double)c->n;  // state 16 + touched 4 + two frontiers 8 + taken mass 8
     const int64_t fit = (int64_t)((double)free_b * pct / 100.0 / per_slot);
@@ -515,12 +515,15 @@ int frontier_plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots)
 int frontier_ensure_slots(arcte_cuda_ctx *c, int64_t want)
 {
     SlotPool &sp = c->slots;
-    if (!(sp.n == c->n && sp.n_slots >= want)) {
+    if (!(sp.n == c->n && sp.n_slots >= want) || sp.compact) {   // (the compact engine leaves its pairs in sr)
         dev_free(sp.sr);
         dev_free(sp.touched);
         dev_free(sp.queue);
+        dev_free(sp.cmap);
+        dev_free(sp.cepoch);
         dev_free(sp.frontier);
         dev_free(sp.fval);
+        sp.compact = false;
         sp.n_slots = sp.queue_slots = sp.frontier_slots = 0;
         sp.queue_cap = 0;
         ARCTE_TRY(dev_reserve(sp.sr, sizeof(double2) * (size_t)want * (size_t)c->n));

@@ -15,6 +15,7 @@
 // with the stable radix sort (key = column, value = weight) so no atomics on doubles and
 // no run-to-run variation.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "primitives.cuh"
@@ -251,6 +252,131 @@ __global__ void k_row_uniform(int64_t n, const NodeInfo *__restrict__ info, cons
     }
 }
 
+// ---- K2c: walk labels ------------------------------------------------------------------------
+// The push kernels keep one dense state array per walk in flight and touch it at random; what bounds them is
+// the number of distinct DRAM lines a walk touches (profiles/r2_engines.md).  A walk's support is, to first
+// order, a union of complete neighbourhoods of the hubs it pushes, so the walks run in a private label space in
+// which the nodes that share their two highest-count neighbours are consecutive: node v sorts by (rank of its
+// best neighbour, rank of its second-best neighbour, v), rank = position in the count-descending node list of
+// K2a.  Only the column indices the push kernels read are renamed -- every row keeps its position and its stored
+// order, so the queue discipline, every sum and the order of the emitted members are what they were
+// (similarity.py:194-216 enqueue in CSR order) -- and members are renamed back when they are emitted.
+__global__ void __launch_bounds__(256)
+k_rank_from_order(int64_t n, const int32_t *__restrict__ order, uint32_t *__restrict__ rank)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rank[order[i]] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+k_hub_keys(int64_t n, const NodeInfo *__restrict__ info, const int32_t *__restrict__ indices,
+           const uint32_t *__restrict__ rank, uint32_t *__restrict__ key1, uint32_t *__restrict__ key2,
+           uint32_t *__restrict__ ids)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const NodeInfo iu = info[row];
+    uint32_t m1 = (uint32_t)n, m2 = (uint32_t)n;   // smallest and second-smallest neighbour rank
+    for (unsigned j = lane_id(); j < iu.len; j += 32) {
+        const uint32_t r = rank[indices[iu.begin + j]];
+        if (r < m1) { m2 = m1; m1 = r; }
+        else if (r < m2 && r != m1) m2 = r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t a1 = __shfl_xor_sync(kFull, m1, o), a2 = __shfl_xor_sync(kFull, m2, o);
+        const uint32_t lo = min(m1, a1), hi = max(m1, a1);
+        m2 = min(hi == lo ? (uint32_t)n : hi, min(m2, a2));
+        m1 = lo;
+    }
+    if (lane_id() == 0) {
+        key1[row] = m1;
+        key2[row] = m2;
+        ids[row] = (uint32_t)row;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_u32(int64_t n, const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+// order[i] = node that gets walk label i
+__global__ void __launch_bounds__(256)
+k_walk_nodes(int64_t n, const uint32_t *__restrict__ order, const NodeInfo *__restrict__ info,
+             const double *__restrict__ row_w, int32_t *__restrict__ to_walk, int32_t *__restrict__ from_walk,
+             NodeInfo *__restrict__ walk_info, double *__restrict__ walk_row_w)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = order[i];
+    to_walk[v] = (int32_t)i;
+    from_walk[i] = (int32_t)v;
+    walk_info[i] = info[v];
+    walk_row_w[i] = row_w[v];
+}
+
+__global__ void __launch_bounds__(256)
+k_walk_indices(int64_t nnz, const int32_t *__restrict__ indices, const int32_t *__restrict__ to_walk,
+               int32_t *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += stride) out[j] = to_walk[indices[j]];
+}
+
+// Needs node_info, row_w and the count-descending node list (c->seeds, all n entries) of select_seeds.
+static int build_walk_labels(arcte_cuda_ctx *c)
+{
+    c->walk_labels_valid = false;
+    const char *env = getenv("ARCTE_CUDA_WALK_LABELS");
+    if (env && !strcmp(env, "0")) return ARCTE_OK;
+    const int64_t n = c->n;
+    cudaStream_t st = c->stream;
+    int64_t *launches = &c->stats.launches;
+    const size_t m = (size_t)n + 1;
+    ARCTE_TRY(dev_reserve(c->walk_info, sizeof(NodeInfo) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->walk_row_w, sizeof(double) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->walk_indices, sizeof(int32_t) * (size_t)(c->nnz > 0 ? c->nnz : 1)));
+    ARCTE_TRY(dev_reserve(c->to_walk, sizeof(int32_t) * (size_t)n));
+    ARCTE_TRY(dev_reserve(c->from_walk, sizeof(int32_t) * (size_t)n));
+    for (int k : {0, 1, 2, 3, 8, 9}) ARCTE_TRY(dev_reserve(c->scratch[k], sizeof(uint32_t) * m));
+    uint32_t *rank = c->scratch[8].as<uint32_t>(), *key1 = c->scratch[9].as<uint32_t>();
+    k_rank_from_order<<<grid_for(n, 256), 256, 0, st>>>(n, c->seeds.as<int32_t>(), rank);
+    k_hub_keys<<<grid_for(n * 32, 256), 256, 0, st>>>(n, c->node_info.as<NodeInfo>(), c->indices.as<int32_t>(), rank, key1,
+                                                     c->scratch[0].as<uint32_t>(), c->scratch[2].as<uint32_t>());
+    *launches += 2;
+    const int bits = bit_length((uint64_t)n);
+    bool second = false;
+    ARCTE_TRY(radix_sort_pairs(c->scratch[0].as<uint32_t>(), c->scratch[2].p, c->scratch[1].as<uint32_t>(), c->scratch[3].p,
+                               n, bits, 4, c->scratch[4], c->scratch[5], c->scratch[6], st, &second, launches));
+    // nodes by second-best neighbour; stable sort by the best neighbour on top gives the lexicographic order
+    uint32_t *ids_a = second ? c->scratch[3].as<uint32_t>() : c->scratch[2].as<uint32_t>();
+    uint32_t *ids_b = second ? c->scratch[2].as<uint32_t>() : c->scratch[3].as<uint32_t>();
+    uint32_t *keys_a = second ? c->scratch[1].as<uint32_t>() : c->scratch[0].as<uint32_t>();
+    uint32_t *keys_b = second ? c->scratch[0].as<uint32_t>() : c->scratch[1].as<uint32_t>();
+    k_gather_u32<<<grid_for(n, 256), 256, 0, st>>>(n, key1, ids_a, keys_a);
+    ++*launches;
+    ARCTE_TRY(radix_sort_pairs(keys_a, ids_a, keys_b, ids_b, n, bits, 4, c->scratch[4], c->scratch[5], c->scratch[6], st,
+                               &second, launches));
+    const uint32_t *order = second ? ids_b : ids_a;
+    k_walk_nodes<<<grid_for(n, 256), 256, 0, st>>>(n, order, c->node_info.as<NodeInfo>(), c->row_w.as<double>(),
+                                                  c->to_walk.as<int32_t>(), c->from_walk.as<int32_t>(),
+                                                  c->walk_info.as<NodeInfo>(), c->walk_row_w.as<double>());
+    ++*launches;
+    if (c->nnz > 0) {
+        unsigned g = grid_for(c->nnz, 256);
+        if (g > (unsigned)c->sm_count * 16) g = (unsigned)c->sm_count * 16;
+        k_walk_indices<<<g, 256, 0, st>>>(c->nnz, c->indices.as<int32_t>(), c->to_walk.as<int32_t>(),
+                                          c->walk_indices.as<int32_t>());
+        ++*launches;
+    }
+    ARCTE_CUDA_TRY(cudaGetLastError());
+    c->walk_labels_valid = true;
+    return ARCTE_OK;
+}
+
 // ---- K2a: seeds, count-descending (ties: ascending node id); needs colcnt ----
 int select_seeds(arcte_cuda_ctx *c)
 {
@@ -314,6 +440,7 @@ int select_seeds(arcte_cuda_ctx *c)
                                c->scratch[6], st, &second, launches));
     ARCTE_CUDA_TRY(cudaMemcpyAsync(c->seeds.p, second ? c->scratch[3].p : c->scratch[2].p,
                                    sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    ARCTE_TRY(build_walk_labels(c));
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;

@@ -131,10 +131,11 @@ class Engine:
 
     def set_engine(self, engine="auto", table_capacity=0):
         """Engine of the exact FIFO schedule (include/arcte_cuda.h: ARCTE_ENGINE_*): "auto", "fifo" (one
-        queue entry per warp iteration, dense state), "dense" (batched, dense state) or "hash" (batched,
-        compact per-walk hash tables).  All of them give bit-identical results."""
+        queue entry per warp iteration, dense state), "dense" (batched, dense state), "hash" (batched,
+        compact per-walk hash tables) or "compact" (one entry per iteration, pairs in first-touch order behind an
+        epoch-tagged index map).  All of them give bit-identical results."""
         names = {"auto": _lib.ENGINE_AUTO, "fifo": _lib.ENGINE_FIFO_DENSE, "dense": _lib.ENGINE_BATCHED_DENSE,
-                 "hash": _lib.ENGINE_BATCHED_HASH}
+                 "hash": _lib.ENGINE_BATCHED_HASH, "compact": _lib.ENGINE_FIFO_COMPACT}
         if engine not in names:
             raise ValueError("unknown engine %r" % (engine,))
         check(self._L.arcte_cuda_set_engine(self._h, names[engine], int(table_capacity)))
