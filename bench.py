@@ -270,9 +270,11 @@ def cold_call(A):
 
 # --------------------------------------------------------------------------------------- GPU arm
 ENGINE_NAMES = {-2: "frontier", 0: "fifo (one queue entry per warp iteration, dense state)",
-                1: "batched, direct-mapped 32-byte state", 2: "batched, per-walk hash tables"}
+                1: "batched, direct-mapped 32-byte state", 2: "batched, per-walk hash tables",
+                3: "fifo (one queue entry per warp iteration), compact first-touch-ordered state behind an "
+                   "epoch-tagged index map, walk labels"}
 KERNEL_NAMES = {-2: "k_push_frontier", 0: "k_push_threshold<absorbing>", 1: "k_walk_batched<direct>",
-                2: "k_walk_batched<hash>"}
+                2: "k_walk_batched<hash>", 3: "k_push_compact<absorbing>"}
 
 
 def main():

@@ -62,13 +62,14 @@ enum {
                                     launch geometry).  Absorbing rule (arcte) only. */
 };
 
-/* Engines of the exact FIFO schedule (arcte_cuda_set_engine).  All three replay the reference's queue
+/* Engines of the exact FIFO schedule (arcte_cuda_set_engine).  All four replay the reference's queue
    discipline and arithmetic exactly (bit-identical s, r, push counts and supports); they differ in how
    the walk state is laid out and in how many queue entries one warp iteration takes. */
 enum {
-    ARCTE_ENGINE_AUTO = -1,          /* absorbing rule: BATCHED_DENSE for 4096 <= n <= 2^19, FIFO_DENSE otherwise
-                                        (measured cross-over, profiles/r2_engines.md); PageRank / lazy rules:
-                                        FIFO_DENSE.  Default.                                              */
+    ARCTE_ENGINE_AUTO = -1,          /* FIFO_COMPACT for graphs of 2^22 or more stored entries (all rules); below
+                                        that, absorbing rule: BATCHED_DENSE for 4096 <= n <= 2^19, FIFO_DENSE
+                                        otherwise; PageRank / lazy rules: FIFO_DENSE (measured cross-overs,
+                                        profiles/r2_engines.md, r2_compact_state.md).  Default.             */
     ARCTE_ENGINE_FIFO_DENSE = 0,     /* one queue entry per warp iteration, dense 16-byte {s, r} per node and walk,
                                         32 walks per SM                                                     */
     ARCTE_ENGINE_BATCHED_DENSE = 1,  /* up to 32 queue entries (64 stored entries) per warp iteration, all pop checks

@@ -752,9 +752,10 @@ static void fill_graph_params(const arcte_cuda_ctx *c, PushParams &P, bool walk_
     P.indices = walk_labels ? c->walk_indices.as<int32_t>() : c->indices.as<int32_t>();
     P.row_w = walk_labels ? c->walk_row_w.as<double>() : c->row_w.as<double>();
     P.from_walk = walk_labels ? c->from_walk.as<int32_t>() : nullptr;
+    P.unit_rows = c->unit_rows ? 1 : 0;
 }
 
-constexpr int kCompactWarpsPerSm = 40;   // 5 CTAs of 8 warps at 48 registers (push_compact.cu: ARCTE_COMPACT_MIN_BLOCKS)
+constexpr int kCompactWarpsPerSm = 48;   // 6 CTAs of 8 warps at 40 registers (push_compact.cu: ARCTE_COMPACT_MIN_BLOCKS)
 
 static int bits_for(int64_t v)   // bits needed for values 0 .. v-1 (at least 1)
 {
@@ -876,7 +877,9 @@ static int launch_push(arcte_cuda_ctx *c, int rule, const PushParams &P)
 {
     if (P.cmap) return compact_launch(c, rule, P);
     const unsigned grid = grid_for(P.n_slots * 32, 256);
-    static const bool pipelined = !(getenv("ARCTE_CUDA_PIPELINED") && !strcmp(getenv("ARCTE_CUDA_PIPELINED"), "0"));
+    // experiment switch, off: the pipelined loop needs 80 registers (24 walks per SM) and ends up slower than the
+    // plain loop at 32 walks per SM (profiles/r2_pipelined_fifo.md)
+    static const bool pipelined = getenv("ARCTE_CUDA_PIPELINED") && !strcmp(getenv("ARCTE_CUDA_PIPELINED"), "1");
     switch (rule) {
     case ARCTE_RULE_ABSORBING:
         if (pipelined) k_push_pipelined<ARCTE_RULE_ABSORBING><<<grid, 32 * kPipeWarps, 0, c->stream>>>(P);
@@ -907,9 +910,10 @@ static int64_t compact_cap(const arcte_cuda_ctx *c, bool full)
 }
 
 static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap, bool compact,
-                      bool full_cap = false)
+                      bool full_cap = false, int walks_per_warp = 1)
 {
-    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? kCompactWarpsPerSm : 32);
+    const int wps = (c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? (walks_per_warp > 1 ? 32 : kCompactWarpsPerSm) : 32)) *
+                    walks_per_warp;
     const int64_t ccap = compact ? compact_cap(c, full_cap) : c->n;
     int64_t want = (int64_t)c->sm_count * wps;
     want = ((want + 7) / 8) * 8;
@@ -974,6 +978,7 @@ static int resolve_engine(const arcte_cuda_ctx *c, int rule)
     if (rule != ARCTE_RULE_ABSORBING) {   // the batched engines implement the absorbing rule only
         const char *env = getenv("ARCTE_CUDA_ENGINE");
         if (e == ARCTE_ENGINE_AUTO && env && !strcmp(env, "compact")) e = ARCTE_ENGINE_FIFO_COMPACT;
+        if (e == ARCTE_ENGINE_AUTO && !env && c->nnz >= (int64_t(1) << 22)) e = ARCTE_ENGINE_FIFO_COMPACT;
         return e == ARCTE_ENGINE_FIFO_COMPACT ? e : ARCTE_ENGINE_FIFO_DENSE;
     }
     if (e == ARCTE_ENGINE_AUTO) {
@@ -983,10 +988,14 @@ static int resolve_engine(const arcte_cuda_ctx *c, int rule)
         else if (env && !strcmp(env, "hash")) e = ARCTE_ENGINE_BATCHED_HASH;
         else if (env && !strcmp(env, "compact")) e = ARCTE_ENGINE_FIFO_COMPACT;
     }
-    // measured (profiles/r2_engines.md): the batched direct-mapped engine wins on medium graphs (Flickr shape 134
-    // vs 166 ms, BA(150000,3) 14.6 vs 19.7 ms); tiny graphs and the 1.1 M-node bench shape go to the FIFO engine
-    if (e == ARCTE_ENGINE_AUTO)
-        e = (c->n >= 4096 && c->n <= (int64_t(1) << 19)) ? ARCTE_ENGINE_BATCHED_DENSE : ARCTE_ENGINE_FIFO_DENSE;
+    // measured (profiles/r2_engines.md, r2_compact_state.md): graphs with millions of stored entries are bound by
+    // DRAM accesses and go to the compact-state engine (YouTube shape 605 vs 706 ms, Flickr shape 110 vs 133 / 158 ms);
+    // smaller graphs are bound by their longest walk, where the shorter dependent chain of the dense layouts wins:
+    // the batched direct-mapped engine on medium graphs (BA(150000,3) 13.7 vs 15.6 ms), the FIFO engine on tiny ones
+    if (e == ARCTE_ENGINE_AUTO) {
+        if (c->nnz >= (int64_t(1) << 22)) e = ARCTE_ENGINE_FIFO_COMPACT;
+        else e = (c->n >= 4096 && c->n <= (int64_t(1) << 19)) ? ARCTE_ENGINE_BATCHED_DENSE : ARCTE_ENGINE_FIFO_DENSE;
+    }
     return e;
 }
 
@@ -1066,7 +1075,8 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         ARCTE_TRY(batched_plan(c, engine, S, &n_slots, &qcap));
         ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
     } else {
-        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap, compact));
+        const int wpw = (compact && rule == ARCTE_RULE_ABSORBING) ? 32 / compact_group_lanes() : 1;   // walks per warp
+        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap, compact, false, wpw));
         ARCTE_TRY(ensure_slots(c, n_slots, qcap, compact, compact_cap(c, false)));
     }
     stt.engine = frontier ? -2 : engine;

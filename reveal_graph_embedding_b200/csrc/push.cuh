@@ -77,6 +77,7 @@ struct PushParams {
     int64_t map_stride;        // entries per slot in cmap (n rounded up to a multiple of 4)
     int idx_bits;              // bits of the compact index in a map entry
     int64_t ccap;              // pairs (and touched entries) per slot: a walk that touches more nodes is re-run with ccap = n
+    int unit_rows;             // 1: every transition weight of row u is exactly 1/len(u): recomputed, the weight array is not read
 };
 
 
@@ -88,6 +89,8 @@ int batched_launch(arcte_cuda_ctx *c, int engine, const PushParams &P);
 
 // Implemented in push_compact.cu.
 int compact_launch(arcte_cuda_ctx *c, int rule, const PushParams &P);
+int compact_group_lanes();   // lanes per walk of the absorbing rule's extraction (32: one walk per warp)
+constexpr int kCompactGroupLanes = 32;
 int compact_scatter(arcte_cuda_ctx *c, const PushParams &P, int64_t nt, double *s_dev, double *r_dev);
 
 // Implemented in push_frontier.cu.

@@ -249,6 +249,10 @@ __global__ void k_row_uniform(int64_t n, const NodeInfo *__restrict__ info, cons
     if (lane == 0) {
         row_w[row] = w0;
         if (!same) atomicOr(any_nonuniform, 1ull);
+        // unit adjacency weights: the row sum is the row length and every transition weight is 1/len
+        // (transition.py:61-63), which a push kernel can recompute instead of reading the weight array
+        if (iu.len && (!same || __double_as_longlong(w0) != __double_as_longlong(__ddiv_rn(1.0, (double)iu.len))))
+            atomicOr(any_nonuniform + 1, 1ull);
     }
 }
 
@@ -411,23 +415,24 @@ int select_seeds(arcte_cuda_ctx *c)
     ARCTE_TRY(dev_reserve(c->scratch[1], sizeof(uint32_t) * m));
     ARCTE_TRY(dev_reserve(c->scratch[2], sizeof(uint32_t) * m));
     ARCTE_TRY(dev_reserve(c->scratch[3], sizeof(uint32_t) * m));
-    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * 4));
+    ARCTE_TRY(dev_reserve(c->scratch[7], sizeof(int64_t) * 8));
     ARCTE_TRY(dev_reserve(c->counters, sizeof(int64_t) * PC_COUNT));
     ARCTE_TRY(dev_reserve(c->row_w, sizeof(double) * (size_t)n));
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
     int64_t *tmp2 = c->scratch[7].as<int64_t>();
-    ARCTE_CUDA_TRY(cudaMemsetAsync(tmp2, 0, 3 * sizeof(int64_t), st));
+    ARCTE_CUDA_TRY(cudaMemsetAsync(tmp2, 0, 5 * sizeof(int64_t), st));
     k_count_stats<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), tmp2);
     ++*launches;
     k_row_uniform<<<grid_for(n * 32, 256), 256, 0, st>>>(n, c->node_info.as<NodeInfo>(), c->w.as<double>(),
                                                         c->row_w.as<double>(), (unsigned long long *)(tmp2 + 2));
     ++*launches;
-    int64_t host2[3];
+    int64_t host2[5];
     ARCTE_CUDA_TRY(cudaMemcpyAsync(host2, tmp2, sizeof(host2), cudaMemcpyDeviceToHost, st));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
     const int32_t maxcnt = (int32_t)host2[0];
     c->n_seeds = host2[1];
     c->uniform_rows = host2[2] == 0 && !getenv("ARCTE_CUDA_NO_UNIFORM");
+    c->unit_rows = host2[3] == 0 && !getenv("ARCTE_CUDA_NO_UNIT_ROWS");
     c->row_w_valid = true;
     k_seed_keys<<<grid_for(n, 256), 256, 0, st>>>(n, c->colcnt.as<int32_t>(), maxcnt,
                                                   c->scratch[0].as<uint32_t>(),
