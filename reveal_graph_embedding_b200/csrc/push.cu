@@ -910,10 +910,9 @@ static int64_t compact_cap(const arcte_cuda_ctx *c, bool full)
 }
 
 static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap, bool compact,
-                      bool full_cap = false, int walks_per_warp = 1)
+                      bool full_cap = false)
 {
-    const int wps = (c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? (walks_per_warp > 1 ? 32 : kCompactWarpsPerSm) : 32)) *
-                    walks_per_warp;
+    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? kCompactWarpsPerSm : 32);
     const int64_t ccap = compact ? compact_cap(c, full_cap) : c->n;
     int64_t want = (int64_t)c->sm_count * wps;
     want = ((want + 7) / 8) * 8;
@@ -1075,8 +1074,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         ARCTE_TRY(batched_plan(c, engine, S, &n_slots, &qcap));
         ARCTE_TRY(batched_ensure(c, engine, n_slots, qcap));
     } else {
-        const int wpw = (compact && rule == ARCTE_RULE_ABSORBING) ? 32 / compact_group_lanes() : 1;   // walks per warp
-        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap, compact, false, wpw));
+        ARCTE_TRY(plan_slots(c, S, &n_slots, &qcap, compact));
         ARCTE_TRY(ensure_slots(c, n_slots, qcap, compact, compact_cap(c, false)));
     }
     stt.engine = frontier ? -2 : engine;

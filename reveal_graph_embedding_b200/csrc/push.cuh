@@ -89,8 +89,6 @@ int batched_launch(arcte_cuda_ctx *c, int engine, const PushParams &P);
 
 // Implemented in push_compact.cu.
 int compact_launch(arcte_cuda_ctx *c, int rule, const PushParams &P);
-int compact_group_lanes();   // lanes per walk of the absorbing rule's extraction (32: one walk per warp)
-constexpr int kCompactGroupLanes = 32;
 int compact_scatter(arcte_cuda_ctx *c, const PushParams &P, int64_t nt, double *s_dev, double *r_dev);
 
 // Implemented in push_frontier.cu.

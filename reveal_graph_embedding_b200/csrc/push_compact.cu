@@ -129,72 +129,6 @@ __device__ __forceinline__ int push_node_c(const PushParams &P, uint32_t *__rest
     return PUSH_OK;
 }
 
-// The whole warp pushes one entry of the walk in `wk` whose pair was already read: row [begin, begin+len), s of the
-// node sx, push coefficient c = (1 - rho) r (absorbing rule; the several-walks-per-warp kernel below).
-__device__ __forceinline__ int push_row_c(const PushParams &P, uint32_t *__restrict__ map, double2 *__restrict__ cst,
-                                          int32_t *__restrict__ touched, int2 *__restrict__ queue, CWalk &wk,
-                                          unsigned long long *ws, int ui, double sx, double c, unsigned begin, unsigned len,
-                                          const Threshold &eps, uint32_t tag, uint32_t imask, int lane, unsigned lt)
-{
-    if (lane == 0) {
-        st_state(&cst[ui], make_double2(sx, 0.0));   // push.py:60
-        ws[WS_PUSHES] += 1;
-        ws[WS_EDGES] += len;
-    }
-    __syncwarp();
-    const unsigned qmask = (unsigned)P.queue_cap - 1u;
-    const int32_t *__restrict__ idx = P.indices + begin;
-    const double *__restrict__ wgt = P.w + begin;
-    // unit adjacency weights: every entry of the row is 1/len (transition.py:61-63), one product per push
-    const double p_unit = P.unit_rows ? __dmul_rn(c, __ddiv_rn(1.0, (double)len)) : 0.0;
-    for (unsigned base = 0; base < len; base += 32) {
-        const unsigned j = base + lane;
-        int v = -1;
-        double p = 0.0, dv = 1.0;
-        uint32_t m = 0;
-        if (j < len) {
-            v = ld_index(idx + j);
-            p = P.unit_rows ? p_unit : __dmul_rn(c, ld_weight(wgt + j));
-        }
-        if (v >= 0) {
-            m = ld_map(map + v);
-            dv = ld_info_din(&P.info[v]);
-        }
-        const bool valid = v >= 0 && (m & ~imask) == tag;
-        int vi = (int)(m & imask);
-        double2 o = make_double2(0.0, 0.0);
-        if (valid) o = ld_state(&cst[vi]);
-        double2 nw = o;
-        if (v >= 0) {
-            nw.x = __dadd_rn(o.x, p);   // push.py:63
-            nw.y = __dadd_rn(o.y, p);   // push.py:64
-        }
-        if (valid) st_state(&cst[vi], nw);
-        const bool is_new = v >= 0 && !valid && (nw.x != 0.0 || nw.y != 0.0);
-        const unsigned m_new = __ballot_sync(kFull, is_new);
-        if (wk.nt + __popc(m_new) > (int)P.ccap) return PUSH_CAP;
-        if (is_new) {
-            vi = wk.nt + __popc(m_new & lt);
-            st_map(map + v, tag | (uint32_t)vi);
-            st_state(&cst[vi], nw);
-            touched[vi] = v;
-        }
-        wk.nt += __popc(m_new);
-        const bool enq = (valid || is_new) && quot_ge(nw.y, dv, eps);   // similarity.py:194 / :214
-        const unsigned m_enq = __ballot_sync(kFull, enq);
-        const unsigned cnt = __popc(m_enq);
-        if (cnt) {
-            if (wk.tail - wk.head + cnt > (unsigned)P.queue_cap) return PUSH_RING;
-            if (enq) queue[(wk.tail + __popc(m_enq & lt)) & qmask] = make_int2(v, vi);
-            wk.tail += cnt;
-            if (lane == 0) ws[WS_ENQ] += cnt;
-        }
-    }
-    if (lane == 0 && wk.tail - wk.head > ws[WS_MAXQ]) ws[WS_MAXQ] = wk.tail - wk.head;
-    __syncwarp();
-    return PUSH_OK;
-}
-
 // K4 of one finished walk, by the whole warp: threshold, membership, the per-warp totals.  Nothing is reset.
 template <int RULE>
 __device__ __forceinline__ void threshold_and_emit_c(const PushParams &P, const uint32_t *__restrict__ map,
@@ -433,293 +367,6 @@ k_push_compact(const PushParams P)
     }
 }
 
-// ---- several walks per warp ---------------------------------------------------------------------------------
-// The kernel above keeps a warp on ONE walk.  A pop of that walk is a chain of dependent round trips (ring entry ->
-// node record and pair -> row -> index map -> pair), the pushed node has 7.5 neighbours on average on the bench
-// shape, so three quarters of the lanes idle through every chain, and the launch runs at the latency of those
-// chains: ncu shows DRAM at 30 %, L2 at 23 % and the issue slots at 49 % of their peaks with 13 long-scoreboard
-// stall cycles per issued instruction (profiles/r2_compact_state.md).  Registers cap the warps per SM, so more
-// memory parallelism has to come from inside the warp:
-//   * a warp is split into 32/G groups of G lanes; every group owns a slot and replays one walk of its own, with
-//     the same queue discipline, arithmetic and ordered appends as above (ballots restricted to the group);
-//   * each turn of the loop every group pops one entry and, when the entry passes the threshold and its row has at
-//     most G entries, pushes it -- 32/G independent chains in flight per warp instead of one;
-//   * a row longer than G, and the threshold / membership sweep of a finished walk, are done by the WHOLE warp for
-//     one group at a time with the code of the one-walk kernel (the other groups wait: these phases keep all 32
-//     lanes busy, so nothing is lost).
-// Absorbing rule (arcte).  Results are those of the one-walk kernels, bit for bit.
-#ifndef ARCTE_MULTI_MIN_BLOCKS
-#define ARCTE_MULTI_MIN_BLOCKS 4
-#endif
-
-enum { ST_FETCH = 0, ST_WALK = 1, ST_K4 = 2, ST_ABORT_RING = 3, ST_ABORT_CAP = 4, ST_DONE = 5 };
-
-template <int G>
-__global__ void __launch_bounds__(256, ARCTE_MULTI_MIN_BLOCKS)
-k_push_multi(const PushParams P)
-{
-    constexpr int NG = 32 / G;   // walks per warp
-    constexpr int RULE = ARCTE_RULE_ABSORBING;
-    __shared__ unsigned long long wstat[8][NG + 1][WS_COUNT];   // [group]: the walk in progress, [NG]: totals of the warp
-    const int lane = lane_id();
-    const int wid = threadIdx.x >> 5;
-    const int gid = lane / G, gl = lane % G;
-    const unsigned gmask = G == 32 ? kFull : (((1u << G) - 1u) << (gid * G));
-    const unsigned glt = lanemask_lt() & gmask;
-    const unsigned lt = lanemask_lt();
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp_global * NG >= P.n_slots) return;
-    const int64_t slot = warp_global * NG + gid;
-    const bool slot_ok = slot < P.n_slots;
-    const int64_t myslot = slot_ok ? slot : 0;
-    uint32_t *__restrict__ map = P.cmap + myslot * P.map_stride;
-    double2 *__restrict__ cst = P.sr + myslot * P.ccap;
-    int32_t *__restrict__ touched = P.touched + myslot * P.ccap;
-    int2 *__restrict__ queue = reinterpret_cast<int2 *>(P.queue) + myslot * P.queue_cap;
-    const unsigned qmask = (unsigned)P.queue_cap - 1u;
-    const uint32_t imask = (1u << P.idx_bits) - 1u;
-    const uint32_t epoch_end = 1u << (32 - P.idx_bits);
-    unsigned long long *wtot = wstat[wid][NG];
-    unsigned long long *ws = wstat[wid][gid];
-    if (lane < WS_COUNT) wtot[lane] = 0ull;
-    __syncwarp();
-    if (lane == 0) {
-        unsigned long long t_begin;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-        wtot[WS_T_BEGIN] = t_begin;
-    }
-
-    // state of this lane's group (the same in all its lanes)
-    int st = slot_ok ? ST_FETCH : ST_DONE;
-    uint32_t epoch = slot_ok ? P.cepoch[slot] : 0u;
-    uint32_t tag = 0;
-    unsigned head = 0, tail = 0;
-    int nt = 0, pos = 0, seed = 0;
-    Threshold eps = make_threshold(1.0);
-    // the entry the group is about to push (have): compact index, s of the node, push coefficient, row
-    bool have = false;
-    int ui = 0;
-    double sx = 0.0, cpush = 0.0;
-    unsigned begin = 0, len = 0;
-
-    for (;;) {
-        // ---- (a) groups between walks draw their next seed: one atomic for all of them
-        {
-            const unsigned need = __ballot_sync(kFull, st == ST_FETCH && gl == 0);
-            if (need) {
-                unsigned long long k0 = 0;
-                if (lane == 0) k0 = atomicAdd(&P.counters[PC_WORK_CURSOR], (unsigned long long)__popc(need));
-                k0 = __shfl_sync(kFull, k0, 0);
-                if (st == ST_FETCH) {
-                    const long long k = (long long)k0 + __popc(need & ((1u << (gid * G)) - 1u));
-                    if (k >= P.n_work) {
-                        st = ST_DONE;
-                    } else {
-                        pos = P.work_ids ? P.work_ids[k] : (int)k;
-                        seed = P.work_seed[pos];
-                        eps = make_threshold(P.work_eps[pos]);
-                        if (++epoch >= epoch_end) {   // the epoch field wraps: void the whole map of this slot
-                            uint4 *m4 = reinterpret_cast<uint4 *>(map);
-                            for (int64_t i = gl; i < P.map_stride / 4; i += G) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-                            epoch = 1;
-                        }
-                        tag = epoch << P.idx_bits;
-                        head = tail = 0;
-                        nt = 1;
-                        if (gl < WS_COUNT) ws[gl] = 0ull;
-                        if (G < WS_COUNT && gl == 0)
-                            for (int i = G; i < WS_COUNT; ++i) ws[i] = 0ull;
-                        const NodeInfo iu = ld_info(&P.info[seed]);
-                        if (gl == 0) {
-                            st_map(map + seed, tag);   // compact index 0
-                            st_state(&cst[0], make_double2(1.0, 1.0));   // similarity.py:176-177
-                            touched[0] = seed;
-                        }
-                        // "Do one push for free", similarity.py:183-196
-                        have = true;
-                        ui = 0;
-                        sx = 1.0;
-                        cpush = __dmul_rn(P.one_minus_rho, 1.0);
-                        begin = iu.begin;
-                        len = iu.len;
-                        st = ST_WALK;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (__all_sync(kFull, st == ST_DONE)) break;
-
-        // ---- (b) every walking group without an entry in hand pops one (similarity.py:199-204)
-        if (st == ST_WALK && !have) {
-            if (head == tail) {
-                st = ST_K4;
-            } else {
-                const int2 e = queue[head & qmask];
-                head += 1;
-                const NodeInfo iu = ld_info(&P.info[e.x]);
-                const double2 su = ld_state(&cst[e.y]);
-                if (quot_ge(su.y, iu.d_in, eps)) {
-                    have = true;
-                    ui = e.y;
-                    sx = su.x;
-                    cpush = __dmul_rn(P.one_minus_rho, su.y);   // push.py:57
-                    begin = iu.begin;
-                    len = iu.len;
-                }
-            }
-        }
-
-        // ---- (c) groups whose entry has a row of at most G entries push it themselves
-        {
-            const bool act = st == ST_WALK && have && len <= (unsigned)G;
-            if (__any_sync(kFull, act)) {
-                if (act && gl == 0) {
-                    st_state(&cst[ui], make_double2(sx, 0.0));   // push.py:60
-                    ws[WS_PUSHES] += 1;
-                    ws[WS_EDGES] += len;
-                }
-                __syncwarp();
-                int v = -1;
-                double p = 0.0, dv = 1.0;
-                uint32_t m = 0;
-                if (act && (unsigned)gl < len) {
-                    v = ld_index(P.indices + begin + gl);
-                    p = P.unit_rows ? __dmul_rn(cpush, __ddiv_rn(1.0, (double)len)) : __dmul_rn(cpush, ld_weight(P.w + begin + gl));
-                }
-                if (v >= 0) {
-                    m = ld_map(map + v);
-                    dv = ld_info_din(&P.info[v]);
-                }
-                const bool valid = v >= 0 && (m & ~imask) == tag;
-                int vi = (int)(m & imask);
-                double2 o = make_double2(0.0, 0.0);
-                if (valid) o = ld_state(&cst[vi]);
-                double2 nw = o;
-                if (v >= 0) {
-                    nw.x = __dadd_rn(o.x, p);   // push.py:63
-                    nw.y = __dadd_rn(o.y, p);   // push.py:64
-                }
-                if (valid) st_state(&cst[vi], nw);
-                const bool is_new = v >= 0 && !valid && (nw.x != 0.0 || nw.y != 0.0);
-                const unsigned m_new = __ballot_sync(kFull, is_new) & gmask;
-                const bool enq = (valid || is_new) && quot_ge(nw.y, dv, eps);   // similarity.py:194 / :214
-                const unsigned m_enq = __ballot_sync(kFull, enq) & gmask;
-                const unsigned cnt = __popc(m_enq);
-                if (act) {
-                    if (nt + __popc(m_new) > (int)P.ccap) {
-                        st = ST_ABORT_CAP;
-                    } else if (tail - head + cnt > (unsigned)P.queue_cap) {
-                        // (the pairs of this push are already written; the walk is abandoned, its epoch never used again)
-                        st = ST_ABORT_RING;
-                    } else {
-                        if (is_new) {   // the next compact indices in CSR order = lane order
-                            vi = nt + __popc(m_new & glt);
-                            st_map(map + v, tag | (uint32_t)vi);
-                            st_state(&cst[vi], nw);
-                            touched[vi] = v;
-                        }
-                        nt += __popc(m_new);
-                        if (enq) queue[(tail + __popc(m_enq & glt)) & qmask] = make_int2(v, vi);
-                        tail += cnt;
-                        if (gl == 0) {
-                            ws[WS_ENQ] += cnt;
-                            if (tail - head > ws[WS_MAXQ]) ws[WS_MAXQ] = tail - head;
-                        }
-                    }
-                    have = false;
-                }
-                __syncwarp();
-            }
-        }
-
-        // ---- (d) longer rows: the whole warp pushes them, one group at a time
-        {
-            unsigned longm = __ballot_sync(kFull, st == ST_WALK && have && gl == 0);
-            while (longm) {
-                const int src = __ffs(longm) - 1;   // leader lane of the group
-                longm &= longm - 1;
-                const int64_t gslot = warp_global * NG + src / G;
-                CWalk wk;
-                wk.head = __shfl_sync(kFull, head, src);
-                wk.tail = __shfl_sync(kFull, tail, src);
-                wk.nt = __shfl_sync(kFull, nt, src);
-                Threshold e2;
-                e2.t = __shfl_sync(kFull, eps.t, src);
-                e2.lo = __shfl_sync(kFull, eps.lo, src);
-                e2.hi = __shfl_sync(kFull, eps.hi, src);
-                const int g_ui = __shfl_sync(kFull, ui, src);
-                const double g_sx = __shfl_sync(kFull, sx, src);
-                const double g_r = __ddiv_rn(__shfl_sync(kFull, cpush, src), P.one_minus_rho);   // unused by the push itself
-                (void)g_r;
-                const unsigned g_begin = __shfl_sync(kFull, begin, src);
-                const unsigned g_len = __shfl_sync(kFull, len, src);
-                const uint32_t g_tag = __shfl_sync(kFull, tag, src);
-                const double g_c = __shfl_sync(kFull, cpush, src);
-                const int rc = push_row_c(P, P.cmap + gslot * P.map_stride, P.sr + gslot * P.ccap, P.touched + gslot * P.ccap,
-                                          reinterpret_cast<int2 *>(P.queue) + gslot * P.queue_cap, wk, wstat[wid][src / G], g_ui,
-                                          g_sx, g_c, g_begin, g_len, e2, g_tag, imask, lane, lt);
-                if (lane / G == src / G) {
-                    head = wk.head;
-                    tail = wk.tail;
-                    nt = wk.nt;
-                    have = false;
-                    if (rc != PUSH_OK) st = rc == PUSH_RING ? ST_ABORT_RING : ST_ABORT_CAP;
-                }
-            }
-        }
-
-        // ---- (e) abandoned walks go to the retry pass (nothing to undo: their epoch is never used again)
-        if ((st == ST_ABORT_RING || st == ST_ABORT_CAP)) {
-            if (gl == 0) {
-                const unsigned long long r = atomicAdd(&P.counters[PC_OVERFLOW_SEEDS], 1ull);
-                P.retry_list[r] = pos;
-                atomicAdd(&P.counters[st == ST_ABORT_RING ? PC_QOVERFLOW : PC_TOVERFLOW], 1ull);
-                P.seg_count[pos] = -1;
-            }
-            st = ST_FETCH;
-        }
-
-        // ---- (f) finished walks: threshold and membership by the whole warp, one group at a time
-        {
-            unsigned k4m = __ballot_sync(kFull, st == ST_K4 && gl == 0);
-            while (k4m) {
-                const int src = __ffs(k4m) - 1;
-                k4m &= k4m - 1;
-                const int64_t gslot = warp_global * NG + src / G;
-                const int g_nt = __shfl_sync(kFull, nt, src);
-                const int g_pos = __shfl_sync(kFull, pos, src);
-                const int g_seed = __shfl_sync(kFull, seed, src);
-                const uint32_t g_tag = __shfl_sync(kFull, tag, src);
-                __syncwarp();
-                threshold_and_emit_c<RULE>(P, P.cmap + gslot * P.map_stride, P.sr + gslot * P.ccap, P.touched + gslot * P.ccap,
-                                           g_nt, wstat[wid][src / G], wtot, g_pos, g_seed, g_tag, imask, lane, lt);
-                if (lane / G == src / G) st = ST_FETCH;
-            }
-        }
-    }
-
-    if (slot_ok && gl == 0) P.cepoch[slot] = epoch;
-    __syncwarp();
-    if (lane == 0) {
-        atomicAdd(&P.counters[PC_PUSHES], wtot[WS_PUSHES]);
-        atomicAdd(&P.counters[PC_EDGES], wtot[WS_EDGES]);
-        atomicAdd(&P.counters[PC_ENQUEUES], wtot[WS_ENQ]);
-        atomicMax(&P.counters[PC_MAXQ], wtot[WS_MAXQ]);
-        atomicAdd(&P.counters[PC_SUPPORT], wtot[WS_SUPPORT]);
-        atomicAdd(&P.counters[PC_TOUCHED], wtot[WS_TOUCHED]);
-        atomicAdd(&P.counters[PC_SEEDDEG], wtot[WS_SEEDDEG]);
-        atomicAdd(&P.counters[PC_MEMBERS], wtot[WS_MEMBERS]);
-        atomicAdd(&P.counters[PC_EMITTED], wtot[WS_EMITTED]);
-        unsigned long long t_end;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        atomicMin(&P.counters[PC_T_START], wtot[WS_T_BEGIN]);
-        atomicMax(&P.counters[PC_T_END], t_end);
-        const int my_slots = (int)min((int64_t)NG, P.n_slots - warp_global * NG);
-        atomicAdd(&P.counters[PC_T_BUSY], (t_end - wtot[WS_T_BEGIN]) * (unsigned long long)my_slots);
-    }
-}
-
 // Operator seam: dense s and r of the one walk slot 0 holds (outputs pre-zeroed).
 __global__ void k_compact_scatter(int64_t nt, const int32_t *__restrict__ touched, const double2 *__restrict__ cst,
                                   const int32_t *__restrict__ from_walk, double *__restrict__ s_out,
@@ -734,30 +381,8 @@ __global__ void k_compact_scatter(int64_t nt, const int32_t *__restrict__ touche
     r_out[o] = v.y;
 }
 
-// Walks per warp of the absorbing rule's extraction: ARCTE_CUDA_COMPACT_GROUP = lanes per walk (32, 16 or 8).
-int compact_group_lanes()
-{
-    static int g = -1;
-    if (g < 0) {
-        const char *env = getenv("ARCTE_CUDA_COMPACT_GROUP");
-        g = env ? atoi(env) : kCompactGroupLanes;
-        if (g != 8 && g != 16) g = 32;
-    }
-    return g;
-}
-
 int compact_launch(arcte_cuda_ctx *c, int rule, const PushParams &P)
 {
-    const int G = (rule == ARCTE_RULE_ABSORBING && !P.debug_keep) ? compact_group_lanes() : 32;
-    if (G != 32) {
-        const int64_t warps = (P.n_slots + 32 / G - 1) / (32 / G);
-        const unsigned grid_m = (unsigned)((warps * 32 + 255) / 256);
-        if (G == 16) k_push_multi<16><<<grid_m, 256, 0, c->stream>>>(P);
-        else k_push_multi<8><<<grid_m, 256, 0, c->stream>>>(P);
-        ++c->stats.launches;
-        ARCTE_CUDA_TRY(cudaGetLastError());
-        return ARCTE_OK;
-    }
     const unsigned grid = (unsigned)((P.n_slots * 32 + 255) / 256);
     switch (rule) {
     case ARCTE_RULE_ABSORBING: k_push_compact<ARCTE_RULE_ABSORBING><<<grid, 256, 0, c->stream>>>(P); break;
