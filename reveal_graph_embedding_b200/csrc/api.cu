@@ -174,7 +174,7 @@ void arcte_cuda_destroy(arcte_cuda_ctx *c)
     for (DevBuf *b : fbufs) dev_free(*b);
     for (DevBuf &b : c->peer_stage) dev_free(b);
     DevBuf *pbufs[] = {&c->bpool.tbl, &c->bpool.stage, &c->bpool.clean, &c->bpool.queue, &c->row_w, &c->to_walk, &c->from_walk,
-                       &c->walk_info, &c->walk_row_w, &c->walk_indices, &c->work_seed_w};
+                       &c->walk_info, &c->walk_row_w, &c->walk_indices, &c->work_seed_w, &c->work_order};
     for (DevBuf *b : pbufs) dev_free(*b);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

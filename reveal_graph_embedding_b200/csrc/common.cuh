@@ -191,6 +191,7 @@ struct arcte_cuda_ctx {
     arcte::DevBuf walk_row_w;             // double [n]
     arcte::DevBuf walk_indices;           // int32 [nnz]  column indices in walk labels, rows where and as they were
     arcte::DevBuf work_seed_w;            // int32 [S]  the shard's seeds in walk labels
+    arcte::DevBuf work_order;             // int32 [S]  work-list positions by ascending epsilon-effective (longest walks first)
     bool walk_labels_valid = false;
     bool unit_rows = false;               // every transition weight of row u is exactly 1/len(u)
     arcte::DevBuf counters;  // int64 [PC_COUNT]

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "primitives.cuh"
 #include "push.cuh"
 
 namespace arcte {
@@ -779,6 +780,16 @@ static void fill_compact_params(const arcte_cuda_ctx *c, PushParams &P)
     if (env && atoi(env) >= 2 && 32 - atoi(env) >= P.idx_bits) P.idx_bits = 32 - atoi(env);
 }
 
+// sort key of a walk: the high word of its (positive) epsilon-effective, ascending = longest walks first
+__global__ void k_eps_keys(int64_t n_work, const double *__restrict__ work_eps, uint32_t *__restrict__ keys,
+                           uint32_t *__restrict__ ids)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_work) return;
+    keys[i] = (uint32_t)((unsigned long long)__double_as_longlong(work_eps[i]) >> 32);
+    ids[i] = (uint32_t)i;
+}
+
 __global__ void k_gather_eps(int64_t n_work, int shard_rank, int shard_count,
                              const double *__restrict__ eps_global, double *__restrict__ work_eps)
 {
@@ -1048,10 +1059,27 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
     } else {
         ARCTE_TRY(compute_eps_effective(c, epsilon, c->work_seed.as<int32_t>(), S, c->work_eps.as<double>()));
     }
+    // ---- K2c': work order.  A walk's cost follows 1/epsilon-effective closely (rank correlation 0.997 on the bench
+    // shape, profiles/r2_work_order.json, tools/work_order_study.py) and NOT the seed's count: a seed of count 2 next to a hub gets a tiny epsilon
+    // and one of the longest walks of the run.  Handing the seeds out by ascending epsilon (longest walks first) keeps
+    // the end of the launch -- and, with several GPUs, the wait for the slowest rank -- free of stragglers.
+    const bool frontier = c->schedule == ARCTE_SCHEDULE_FRONTIER;
+    const bool ordered = !frontier && S > 1 && !(getenv("ARCTE_CUDA_WORK_ORDER") && !strcmp(getenv("ARCTE_CUDA_WORK_ORDER"), "0"));
+    if (ordered) {
+        for (int k = 0; k < 4; ++k) ARCTE_TRY(dev_reserve(c->scratch[k], sizeof(uint32_t) * S1));
+        ARCTE_TRY(dev_reserve(c->work_order, sizeof(int32_t) * S1));
+        k_eps_keys<<<grid_for(S, 256), 256, 0, st>>>(S, c->work_eps.as<double>(), c->scratch[0].as<uint32_t>(),
+                                                     c->scratch[2].as<uint32_t>());
+        ++stt.launches;
+        bool second = false;
+        ARCTE_TRY(radix_sort_pairs(c->scratch[0].as<uint32_t>(), c->scratch[2].p, c->scratch[1].as<uint32_t>(), c->scratch[3].p,
+                                   S, 32, 4, c->scratch[4], c->scratch[5], c->scratch[6], st, &second, &stt.launches));
+        ARCTE_CUDA_TRY(cudaMemcpyAsync(c->work_order.p, second ? c->scratch[3].p : c->scratch[2].p, sizeof(int32_t) * (size_t)S,
+                                       cudaMemcpyDeviceToDevice, st));
+    }
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
 
     // ---- slot pool + member buffer ----
-    const bool frontier = c->schedule == ARCTE_SCHEDULE_FRONTIER;
     if (frontier && rule != ARCTE_RULE_ABSORBING) {
         set_error("extract: the frontier schedule implements the absorbing rule (arcte) only");
         return ARCTE_E_ARG;
@@ -1108,7 +1136,7 @@ int extract_shard(arcte_cuda_ctx *c, int rule, double rho, double epsilon, int s
         P.work_seed = c->work_seed_w.as<int32_t>();
     }
     P.work_eps = c->work_eps.as<double>();
-    P.work_ids = nullptr;
+    P.work_ids = ordered ? c->work_order.as<int32_t>() : nullptr;
     P.n_work = S;
     P.retry_pass = 0;
     P.sr = c->slots.sr.as<double2>();
