@@ -1,6 +1,8 @@
 // api.cu -- the extern "C" boundary declared in include/arcte_cuda.h.
+#include <stdio.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -24,7 +26,12 @@ int dev_reserve(DevBuf &b, size_t bytes)
         b.p = nullptr;
         b.bytes = 0;
     }
+    static const bool dbg = getenv("ARCTE_CUDA_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (dbg && bytes >= (size_t(64) << 20))
+        fprintf(stderr, "[arcte] cudaMalloc %.2f GB: %.1f ms\n", 1e-9 * (double)bytes,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
@@ -133,7 +140,7 @@ int arcte_cuda_create(arcte_cuda_ctx **out, int device_id)
     ARCTE_CUDA_TRY(cudaEventCreate(&c->xev1));
     {   // Experiment switch, off by default: ARCTE_CUDA_L2_PERSIST_MB=<n> sets n MB of L2 aside for persisting
         // accesses to the graph arena (upload_structure).  Measured on the bench shape it is a loss: the walks'
-        // own state needs the capacity more (profiles/r2_l2_persist.md).
+        // own state needs the capacity more (profiles/r2_engines.md, item 7).
         const char *env = getenv("ARCTE_CUDA_L2_PERSIST_MB");
         size_t want = env ? (size_t)atol(env) << 20 : 0;
         if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;

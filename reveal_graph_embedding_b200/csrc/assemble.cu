@@ -11,6 +11,11 @@
 // The output is what scipy returns: sorted column indices per row, no duplicates,
 // float64 data (1.0; 2.0 on the diagonal of a node with a self loop), column id of a
 // community = n + seed node id (arcte.py:376).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+
 #include "common.cuh"
 #include "primitives.cuh"
 
@@ -185,6 +190,16 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
     cudaStream_t st = c->stream;
     int64_t *launches = &c->stats.launches;
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev0, st));
+    // ARCTE_CUDA_DEBUG: host clock at the phase boundaries (the extra synchronisations exist only then)
+    static const bool dbg = getenv("ARCTE_CUDA_DEBUG") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[arcte] assemble: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
 
     DevBuf &cnt_by_node = c->scratch[8];
     DevBuf &colptr = c->scratch[9];
@@ -219,6 +234,7 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
     int64_t L = 0;
     ARCTE_CUDA_TRY(cudaMemcpyAsync(&L, colptr.as<int64_t>() + n, sizeof(L), cudaMemcpyDeviceToHost, st));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    phase("sizes + scan");
 
     // 2. pairs in column order, row histogram, stable sort by row
     const size_t L1 = (size_t)(L > 0 ? L : 1);
@@ -238,6 +254,7 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
                 c->scratch[2].as<uint32_t>(), rowcnt.as<int32_t>());
         ++*launches;
     }
+    phase("scratch + gather segments");
     bool second = false;
     ARCTE_TRY(radix_sort_pairs(c->scratch[0].as<uint32_t>(), c->scratch[2].p, c->scratch[1].as<uint32_t>(),
                                c->scratch[3].p, L, bit_length((uint64_t)(nr > 0 ? nr - 1 : 0)), 4,
@@ -245,6 +262,7 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
     const uint32_t *rows = second ? c->scratch[1].as<uint32_t>() : c->scratch[0].as<uint32_t>();
     const uint32_t *cols = second ? c->scratch[3].as<uint32_t>() : c->scratch[2].as<uint32_t>();
 
+    phase("radix sort by row");
     // 3. row lengths -> output row pointers
     k_row_lengths<<<grid_for(nr1, 256), 256, 0, st>>>(nr, row_lo, c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
                                                     rowcnt.as<int32_t>(), base_len.as<int32_t>(),
@@ -259,6 +277,7 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
     ARCTE_TRY(dev_reserve(c->out_indices, sizeof(int32_t) * (size_t)(nnz_out > 0 ? nnz_out : 1)));
     ARCTE_TRY(dev_reserve(c->out_data, sizeof(double) * (size_t)(nnz_out > 0 ? nnz_out : 1)));
 
+    phase("row pointers + output allocation");
     // 4. fill
     k_fill_base<<<grid_for(nr1 * 32, 256), 256, 0, st>>>(nr, row_lo, c->indptr.as<int64_t>(), c->indices.as<int32_t>(),
                                                        diag_pos.as<int32_t>(), c->out_indptr.as<int64_t>(),
@@ -273,6 +292,7 @@ int assemble_parts(arcte_cuda_ctx *c, int n_parts, const SegPart *parts, int64_t
     ARCTE_CUDA_TRY(cudaGetLastError());
     ARCTE_CUDA_TRY(cudaEventRecord(c->ev1, st));
     ARCTE_CUDA_TRY(cudaStreamSynchronize(st));
+    phase("fill base + local");
     float ms = 0.f;
     ARCTE_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats.ms_assemble = ms;

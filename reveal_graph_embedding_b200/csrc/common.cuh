@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/arcte_cuda.h"
@@ -103,10 +104,11 @@ struct BatchedPool {
 // worker thread.
 constexpr int kMaxCopyThreads = 16;
 struct HostRing {
-    void *pinned = nullptr;
+    void *pinned[kMaxCopyThreads] = {};   // per copy thread: two slots of kSlotBytes, allocated once, never moved
     int n_threads = 0;
     cudaStream_t streams[kMaxCopyThreads] = {};
     cudaEvent_t events[2 * kMaxCopyThreads] = {};
+    std::mutex mutex;                     // growth
 };
 int copy_to_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);
 int copy_from_host(arcte_cuda_ctx *c, void *dst, const void *src, size_t bytes);

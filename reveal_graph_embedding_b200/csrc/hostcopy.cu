@@ -11,11 +11,14 @@
 #include <sys/mman.h>
 #include <sys/uio.h>
 #include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -45,34 +48,40 @@ static void advise_huge(void *p, size_t bytes)
     if (hi > lo) (void)madvise((void *)lo, hi - lo, MADV_HUGEPAGE);  // best effort
 }
 
+// Slots are allocated per copy thread and never re-allocated: growing the ring costs only the new threads' slots
+// (page-locking is about 0.5 ms per MB, and the first call of a process grows the ring as its copies get larger).
 static int ensure_ring(arcte_cuda_ctx *c, int threads)
 {
     HostRing &r = c->ring;
-    if (r.pinned && r.n_threads >= threads) return ARCTE_OK;
-    if (r.pinned) {
-        cudaFreeHost(r.pinned);
-        r.pinned = nullptr;
-    }
-    ARCTE_CUDA_TRY(cudaHostAlloc(&r.pinned, (size_t)threads * 2 * kSlotBytes, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lock(r.mutex);
+    if (r.n_threads >= threads) return ARCTE_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int before = r.n_threads;
     for (int t = r.n_threads; t < threads; ++t) {
+        ARCTE_CUDA_TRY(cudaHostAlloc(&r.pinned[t], 2 * kSlotBytes, cudaHostAllocPortable));
         ARCTE_CUDA_TRY(cudaStreamCreateWithFlags(&r.streams[t], cudaStreamNonBlocking));
         ARCTE_CUDA_TRY(cudaEventCreateWithFlags(&r.events[2 * t], cudaEventDisableTiming));
         ARCTE_CUDA_TRY(cudaEventCreateWithFlags(&r.events[2 * t + 1], cudaEventDisableTiming));
+        r.n_threads = t + 1;
     }
-    r.n_threads = threads;
+    if (getenv("ARCTE_CUDA_DEBUG"))
+        fprintf(stderr, "[arcte] pinned ring %d -> %d threads x 2 x 4 MB: %.1f ms\n", before, threads,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return ARCTE_OK;
 }
 
 void free_ring(arcte_cuda_ctx *c)
 {
     HostRing &r = c->ring;
+    std::lock_guard<std::mutex> lock(r.mutex);
     for (int t = 0; t < r.n_threads; ++t) {
         cudaStreamDestroy(r.streams[t]);
         cudaEventDestroy(r.events[2 * t]);
         cudaEventDestroy(r.events[2 * t + 1]);
+        if (r.pinned[t]) cudaFreeHost(r.pinned[t]);
+        r.pinned[t] = nullptr;
     }
-    if (r.pinned) cudaFreeHost(r.pinned);
-    r = HostRing();
+    r.n_threads = 0;
 }
 
 static bool is_pinned(const void *p)
@@ -145,7 +154,7 @@ static int run_jobs(arcte_cuda_ctx *c, const std::vector<CopyJob> &jobs, double 
     HostRing &r = c->ring;
     auto worker = [&](int t) {
         if (cudaSetDevice(c->device) != cudaSuccess) { failed = 1; return; }
-        char *slot[2] = {(char *)r.pinned + (size_t)(2 * t) * kSlotBytes, (char *)r.pinned + (size_t)(2 * t + 1) * kSlotBytes};
+        char *slot[2] = {(char *)r.pinned[t], (char *)r.pinned[t] + kSlotBytes};
         cudaStream_t st = r.streams[t];
         int k = 0;
         Chunk pending{};   // device -> host chunk whose slot still has to be copied out
