@@ -304,6 +304,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO set by the caller) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from reveal_graph_embedding_b200 import distributed as ardist
