@@ -19,7 +19,7 @@ from reveal_graph_embedding_b200.engine import Engine  # noqa: E402
 
 A = make_graph(sys.argv[1] if len(sys.argv) > 1 else "youtube")
 eng = Engine(0)
-eng.set_engine("fifo")
+eng.set_engine("compact")
 eng.configure(warps_per_sm=8, mem_percent=20)
 eng.set_graph(A)                       # K1 + K2a
 eng.extract(0, RHO, EPS)               # K2b + K3/K4 (the push kernel is not in ncu's filter)
