@@ -211,7 +211,21 @@ def arcte_distributed(A, rule, rho_eff, epsilon, engine=None, upload=True, all_r
     ensure_communicator(eng)
     mark("set_graph")
     n = eng.n
-    eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
+    # the self-loop rows (identity entry 2.0, arcte.py:676-679) depend on the input only: found on a side thread
+    # while the device walks (a failure there is met again, and raised, by patch_self_loops)
+    import threading
+
+    def _loops():
+        try:
+            eng.self_loop_rows()
+        except Exception:
+            pass
+    side = threading.Thread(target=_loops)
+    side.start()
+    try:
+        eng.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=world)
+    finally:
+        side.join()
     mark("extract")
     nnz = eng.exchange_assemble()
     mark("exchange+assemble")

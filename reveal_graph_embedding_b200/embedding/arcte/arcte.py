@@ -36,6 +36,13 @@ from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, Engine, canonic
                        get_engine)
 
 
+def _quietly(fn):
+    try:
+        fn()
+    except Exception:
+        pass
+
+
 def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     A = canonical_csr(adjacency_matrix)
     rho_eff = rho  # the lazy_rho substitution of arcte.py:109 happens inside the library
@@ -52,8 +59,15 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
         eng = get_engine(0)
         t = [time.perf_counter()]
         eng.set_graph(A, canonical=True); t.append(time.perf_counter())
-        eng.extract(rule, rho_eff, epsilon); t.append(time.perf_counter())
-        eng.assemble(); t.append(time.perf_counter())
+        # the rows with a stored diagonal (their identity entry is 2.0, arcte.py:676-679) depend on the input only:
+        # found on a side thread while the device walks (a failure there is met again, and raised, by features())
+        side = threading.Thread(target=_quietly, args=(eng.self_loop_rows,))
+        side.start()
+        try:
+            eng.extract(rule, rho_eff, epsilon); t.append(time.perf_counter())
+            eng.assemble(); t.append(time.perf_counter())
+        finally:
+            side.join()
         X = eng.features(); t.append(time.perf_counter())
         if os.environ.get("ARCTE_CUDA_DEBUG"):
             import sys
@@ -88,11 +102,20 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
     def walk(rank):
         e = engines[rank]
         e.set_graph(A, canonical=True)
-        e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
+        if rank == 0:   # self-loop rows of the input (arcte.py:676-679), once, while the devices walk; shared below
+            side = threading.Thread(target=_quietly, args=(e.self_loop_rows,))
+            side.start()
+        try:
+            e.extract(rule, rho_eff, epsilon, shard_rank=rank, shard_count=n_gpus)
+        finally:
+            if rank == 0:
+                side.join()
 
     dbg = os.environ.get("ARCTE_CUDA_DEBUG")
     t0 = time.perf_counter()
     run_parallel(walk)
+    for e in engines[1:]:
+        e._loops = engines[0]._loops   # same input matrix on every GPU
     t1 = time.perf_counter()
     # one exchange step inside the library: NCCL all-to-all of the communities split by row block, then
     # every GPU assembles its own rows (csrc/exchange.cu)

@@ -208,3 +208,70 @@ def test_cli_undirected_flag_forms():
     assert parser.parse_args(base + ["-u"]).undirected is True
     assert parser.parse_args(base + ["-u", "true"]).undirected is True
     assert parser.parse_args(base + ["-u", "False"]).undirected is False
+
+
+def _engine_shell(A):
+    """An Engine with the host-side copies set_graph keeps, without a device (self-loop logic is pure numpy)."""
+    from reveal_graph_embedding_b200.engine import Engine
+    e = Engine.__new__(Engine)
+    e.n, e.nnz, e._loops = int(A.shape[0]), int(A.nnz), None
+    e._indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    e._indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+    return e
+
+
+def test_self_loop_rows_and_patch_match_the_reference_base_block():
+    """arcte.py:676-679: base = I + pattern(A) stores 2.0 where A stores its diagonal.  The host patches those
+    entries into a value array of ones; positions checked against scipy's own I + pattern(A), whole matrix and
+    row blocks, from the main thread and from a side thread (as arcte() runs it)."""
+    import threading
+    from reveal_graph_embedding_b200 import graphs
+    A = graphs.barabasi_albert(500, 3, seed=3).tolil()
+    loops = [0, 1, 17, 250, 499]
+    for i in loops:
+        A[i, i] = 0.5
+    A = sparse.csr_matrix(A)
+    A.sort_indices()
+    n = A.shape[0]
+    pattern = sparse.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
+    base = (sparse.identity(n, format="csr") + pattern).tocsr()
+    base.sort_indices()
+    e = _engine_shell(A)
+    th = threading.Thread(target=e.self_loop_rows)
+    th.start()
+    th.join()
+    rows, rank = e._loops
+    assert rows.tolist() == loops
+    data = np.ones(base.nnz)
+    e.patch_self_loops(data, base.indptr.astype(np.int64))
+    assert np.array_equal(data, base.data)
+    # row blocks, the way the multi-GPU paths patch their slices
+    data2 = np.ones(base.nnz)
+    for lo, hi in ((0, 100), (100, 260), (260, 500)):
+        o0, o1 = base.indptr[lo], base.indptr[hi]
+        e.patch_self_loops(data2[o0:o1], (base.indptr[lo:hi + 1] - o0).astype(np.int64), lo, hi)
+    assert np.array_equal(data2, base.data)
+    # no self loops: nothing is touched
+    B = sparse.csr_matrix(graphs.barabasi_albert(200, 2, seed=4))
+    eb = _engine_shell(B)
+    ones = np.ones(10)
+    eb.patch_self_loops(ones, np.zeros(B.shape[0] + 1, dtype=np.int64))
+    assert eb._loops[0].size == 0 and np.all(ones == 1.0)
+
+
+def test_ones_mapping_is_ordinary_writable_memory():
+    """hostmem.ones: copy-on-write mappings of one block of ones -- reads 1.0 everywhere, writes stay private to
+    the array, a second array is unaffected, small arrays are plain numpy."""
+    from reveal_graph_embedding_b200 import hostmem
+    count = (5 << 20) + 12345          # > 32 MB of doubles: several mappings of the template, ragged end
+    a = hostmem.ones(count)
+    assert a.dtype == np.float64 and a.shape == (count,) and a.flags.writeable
+    assert a[0] == 1.0 and a[-1] == 1.0 and float(a.sum()) == float(count)
+    a[::4096] = 2.0
+    a[-1] = 7.0
+    b = hostmem.ones(count)
+    assert float(b.sum()) == float(count) and b[-1] == 1.0 and b[0] == 1.0
+    assert a[4096] == 2.0 and a[-1] == 7.0
+    small = hostmem.ones(100)
+    assert isinstance(small, np.ndarray) and small.sum() == 100.0
+    del a, b
