@@ -138,9 +138,10 @@ def cpu_reference_run(A, n_threads, target_seconds, sample_hint=None):
         t0 = time.perf_counter()
         sd, seg, mem, eff, st = O.extract(g, 0, RHO, EPS, seeds[idx], n_threads)
         dt = time.perf_counter() - t0
-        if dt >= 0.5 * target_seconds or idx.size >= seeds.size:
+        if dt >= 0.4 * target_seconds or idx.size >= seeds.size:
             break
-        k = int(min(seeds.size, max(k * 2, k * target_seconds / max(dt, 1e-3))))
+        # aim the walks at 0.6 of the target: the assembly of the sample's communities takes about half as long again
+        k = int(min(seeds.size, max(k * 2, k * 0.6 * target_seconds / max(dt, 1e-3))))
     t0 = time.perf_counter()
     O.assemble(g, sd, seg, mem)
     t_asm = time.perf_counter() - t0
@@ -150,7 +151,7 @@ def cpu_reference_run(A, n_threads, target_seconds, sample_hint=None):
             "sample": "%d of %d seeds (evenly spaced over the degree-sorted seed list): transition build %.2f s (whole "
                       "graph, 1 thread) + walks and thresholds %.1f s on the sample, extrapolated linearly in the seed count, + "
                       "assembly of the sample %.2f s (not extrapolated)" % (idx.size, seeds.size, t_graph, dt, t_asm),
-            "walk_only_seeds_per_s": idx.size / dt}, seeds.size
+            "walk_only_seeds_per_s": idx.size / dt, "sample_seeds": int(idx.size)}, seeds.size
 
 
 def _python_reference_worker(args):
@@ -205,8 +206,14 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     n_seeds = 0
     vals = []
+    # every step walks a bounded sample sized so that the WHOLE run (warm-up + steps) ends within a few minutes
+    # whatever --steps/--warmup the caller passes (ARCTE_BENCH_REF_BUDGET_S, default 240 s of CPU arm in total)
+    budget = float(os.environ.get("ARCTE_BENCH_REF_BUDGET_S", "240"))
+    per_step = max(2.0, min(args.cpu_seconds, budget / max(1, args.warmup + args.steps)))
+    hint = None
     for i in range(args.warmup + args.steps):
-        res, n_seeds = cpu_reference_run(A, cores, args.cpu_seconds)
+        res, n_seeds = cpu_reference_run(A, cores, per_step, hint)
+        hint = res["sample_seeds"]   # the next step starts from the sample size this one settled on
         if i >= args.warmup:
             vals.append(res)
     v = float(np.mean([r["value"] for r in vals]))
