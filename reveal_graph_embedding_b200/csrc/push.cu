@@ -756,7 +756,7 @@ static void fill_graph_params(const arcte_cuda_ctx *c, PushParams &P, bool walk_
     P.unit_rows = c->unit_rows ? 1 : 0;
 }
 
-constexpr int kCompactWarpsPerSm = 48;   // 6 CTAs of 8 warps at 40 registers (push_compact.cu: ARCTE_COMPACT_MIN_BLOCKS)
+constexpr int kCompactWarpsPerSm = 8 * ARCTE_COMPACT_MIN_BLOCKS;   // 6 CTAs of 8 warps at 40 registers (push.cuh)
 
 static int bits_for(int64_t v)   // bits needed for values 0 .. v-1 (at least 1)
 {

@@ -7,6 +7,12 @@
 
 #include "common.cuh"
 
+// Compact engine (push_compact.cu): resident CTAs of 8 warps per SM the kernel is compiled for (6 -> 40 registers,
+// 48 walks per SM: the measured optimum of 4 / 5 / 6, profiles/r2_compact_state.md); the slot pool follows it.
+#ifndef ARCTE_COMPACT_MIN_BLOCKS
+#define ARCTE_COMPACT_MIN_BLOCKS 6
+#endif
+
 namespace arcte {
 
 // Walk-state entry of the batched engines: ONE 32-byte sector per touched node, read and written with

@@ -232,10 +232,6 @@ __device__ __forceinline__ void threshold_and_emit_c(const PushParams &P, const 
     __syncwarp();
 }
 
-#ifndef ARCTE_COMPACT_MIN_BLOCKS
-#define ARCTE_COMPACT_MIN_BLOCKS 6
-#endif
-
 template <int RULE>
 __global__ void __launch_bounds__(256, ARCTE_COMPACT_MIN_BLOCKS)
 k_push_compact(const PushParams P)
