@@ -281,7 +281,7 @@ ENGINE_NAMES = {-2: "frontier", 0: "fifo (one queue entry per warp iteration, de
                 3: "fifo (one queue entry per warp iteration), compact first-touch-ordered state behind an "
                    "epoch-tagged index map, walk labels"}
 KERNEL_NAMES = {-2: "k_push_frontier", 0: "k_push_threshold<absorbing>", 1: "k_walk_batched<direct>",
-                2: "k_walk_batched<hash>", 3: "k_push_compact<absorbing>"}
+                2: "k_walk_batched<hash>", 3: "k_push_compact<absorbing, 6 or 8 CTAs per SM>"}
 
 
 def main():
@@ -450,11 +450,12 @@ def main():
     engine_id = int(st.get("engine", 0))
     # DRAM bytes of one launch of the same kernel on the same workload from the committed ncu capture
     # (per launch, like `achieved`); null for any other configuration.
-    traffic = None
+    traffic = traffic_note = None
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "r2_push_youtube_traffic.json")))
         if args.workload == cap["workload"] and world == cap["n_gpus"] and engine_id == cap["engine"]:
             traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+            traffic_note = cap.get("note")
     except (OSError, KeyError, ValueError):
         pass
     achieved = alg_job / (push_ms_job / 1e3) / 1e9 / world  # per GPU: each GPU ran alg_job/world bytes
@@ -464,6 +465,8 @@ def main():
                 "pushes": st["pushes"], "edge_touches": st["edge_touches"], "support": st["support"],
                 "note": "achieved = SURVEY 8(d) algorithmic bytes of this GPU's seeds / push-kernel time "
                         "(CUDA events on the launching stream)"}
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
     cfg = describe(args.workload, A, n_seeds, eps)
     cfg["engine"] = ENGINE_NAMES.get(engine_id, str(engine_id))
     mean_stage = [float(x) for x in np.mean(np.array(stage_ms), axis=0)]

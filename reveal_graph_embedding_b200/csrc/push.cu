@@ -756,7 +756,9 @@ static void fill_graph_params(const arcte_cuda_ctx *c, PushParams &P, bool walk_
     P.unit_rows = c->unit_rows ? 1 : 0;
 }
 
-constexpr int kCompactWarpsPerSm = 8 * ARCTE_COMPACT_MIN_BLOCKS;   // 6 CTAs of 8 warps at 40 registers (push.cuh)
+constexpr int kCompactWarpsPerSm = 8 * ARCTE_COMPACT_MIN_BLOCKS;       // 6 CTAs of 8 warps at 40 registers (push.cuh)
+constexpr int kCompactWarpsPerSmHi = 8 * ARCTE_COMPACT_MIN_BLOCKS_HI;  // 8 CTAs at 32 registers: graphs of short rows
+constexpr int64_t kShortRowMean = 16;                                   // stored entries per row below which a graph takes the latter
 
 static int bits_for(int64_t v)   // bits needed for values 0 .. v-1 (at least 1)
 {
@@ -923,7 +925,9 @@ static int64_t compact_cap(const arcte_cuda_ctx *c, bool full)
 static int plan_slots(arcte_cuda_ctx *c, int64_t n_work, int64_t *n_slots, int64_t *queue_cap, bool compact,
                       bool full_cap = false)
 {
-    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm : (compact ? kCompactWarpsPerSm : 32);
+    const bool short_rows = c->nnz < kShortRowMean * c->n;
+    const int wps = c->warps_per_sm > 0 ? c->warps_per_sm
+                                        : (compact ? (short_rows ? kCompactWarpsPerSmHi : kCompactWarpsPerSm) : 32);
     const int64_t ccap = compact ? compact_cap(c, full_cap) : c->n;
     int64_t want = (int64_t)c->sm_count * wps;
     want = ((want + 7) / 8) * 8;

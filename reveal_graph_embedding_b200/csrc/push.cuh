@@ -7,10 +7,16 @@
 
 #include "common.cuh"
 
-// Compact engine (push_compact.cu): resident CTAs of 8 warps per SM the kernel is compiled for (6 -> 40 registers,
-// 48 walks per SM: the measured optimum of 4 / 5 / 6, profiles/r2_compact_state.md); the slot pool follows it.
+// Compact engine (push_compact.cu): the kernel is compiled for two occupancy points, 6 resident CTAs of 8 warps per
+// SM (40 registers, 48 walks per SM) and 8 (32 registers, 64 walks per SM).  Measured on one B200
+// (profiles/r2_occupancy_ab.md): graphs of short rows are latency-bound and gain from more walks in flight (YouTube
+// shape, 5.3 entries per row: 591 -> 572 ms at 64), graphs of long rows lose (Flickr shape, 146 per row: 109 -> 114 ms).
+// The slot pool follows the choice (plan_slots); the launch picks the instantiation that matches the pool.
 #ifndef ARCTE_COMPACT_MIN_BLOCKS
 #define ARCTE_COMPACT_MIN_BLOCKS 6
+#endif
+#ifndef ARCTE_COMPACT_MIN_BLOCKS_HI
+#define ARCTE_COMPACT_MIN_BLOCKS_HI 8
 #endif
 
 namespace arcte {

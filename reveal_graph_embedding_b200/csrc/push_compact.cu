@@ -232,8 +232,8 @@ __device__ __forceinline__ void threshold_and_emit_c(const PushParams &P, const 
     __syncwarp();
 }
 
-template <int RULE>
-__global__ void __launch_bounds__(256, ARCTE_COMPACT_MIN_BLOCKS)
+template <int RULE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 k_push_compact(const PushParams P)
 {
     __shared__ unsigned long long wstat[8][2][WS_COUNT];
@@ -380,10 +380,22 @@ __global__ void k_compact_scatter(int64_t nt, const int32_t *__restrict__ touche
 int compact_launch(arcte_cuda_ctx *c, int rule, const PushParams &P)
 {
     const unsigned grid = (unsigned)((P.n_slots * 32 + 255) / 256);
+    // more walk states than 6 CTAs per SM can hold: the 32-register instantiation keeps all of them resident
+    const bool hi = P.n_slots > (int64_t)c->sm_count * 8 * ARCTE_COMPACT_MIN_BLOCKS;
+    constexpr int LO = ARCTE_COMPACT_MIN_BLOCKS, HI = ARCTE_COMPACT_MIN_BLOCKS_HI;
     switch (rule) {
-    case ARCTE_RULE_ABSORBING: k_push_compact<ARCTE_RULE_ABSORBING><<<grid, 256, 0, c->stream>>>(P); break;
-    case ARCTE_RULE_PAGERANK: k_push_compact<ARCTE_RULE_PAGERANK><<<grid, 256, 0, c->stream>>>(P); break;
-    case ARCTE_RULE_LAZY: k_push_compact<ARCTE_RULE_LAZY><<<grid, 256, 0, c->stream>>>(P); break;
+    case ARCTE_RULE_ABSORBING:
+        if (hi) k_push_compact<ARCTE_RULE_ABSORBING, HI><<<grid, 256, 0, c->stream>>>(P);
+        else k_push_compact<ARCTE_RULE_ABSORBING, LO><<<grid, 256, 0, c->stream>>>(P);
+        break;
+    case ARCTE_RULE_PAGERANK:
+        if (hi) k_push_compact<ARCTE_RULE_PAGERANK, HI><<<grid, 256, 0, c->stream>>>(P);
+        else k_push_compact<ARCTE_RULE_PAGERANK, LO><<<grid, 256, 0, c->stream>>>(P);
+        break;
+    case ARCTE_RULE_LAZY:
+        if (hi) k_push_compact<ARCTE_RULE_LAZY, HI><<<grid, 256, 0, c->stream>>>(P);
+        else k_push_compact<ARCTE_RULE_LAZY, LO><<<grid, 256, 0, c->stream>>>(P);
+        break;
     default: set_error("unknown push rule"); return ARCTE_E_ARG;
     }
     ++c->stats.launches;
