@@ -311,8 +311,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO set by the caller) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries ONE JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO set by the caller) goes to stderr.
+        # NCCL opens the file with "w": not when stderr is a regular file, which that would truncate.
+        import stat
+        try:
+            if not stat.S_ISREG(os.fstat(2).st_mode):
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        except OSError:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from reveal_graph_embedding_b200 import distributed as ardist
