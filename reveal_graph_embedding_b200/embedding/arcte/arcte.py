@@ -36,6 +36,9 @@ from ...engine import (RULE_ABSORBING, RULE_LAZY, RULE_PAGERANK, Engine, canonic
                        get_engine)
 
 
+_SIDE_THREAD_MIN_NNZ = 1 << 20   # below this a thread costs more than the scan it hides
+
+
 def _quietly(fn):
     try:
         fn()
@@ -61,13 +64,15 @@ def _extract_features(adjacency_matrix, rho, epsilon, number_of_threads, rule):
         eng.set_graph(A, canonical=True); t.append(time.perf_counter())
         # the rows with a stored diagonal (their identity entry is 2.0, arcte.py:676-679) depend on the input only:
         # found on a side thread while the device walks (a failure there is met again, and raised, by features())
-        side = threading.Thread(target=_quietly, args=(eng.self_loop_rows,))
-        side.start()
+        side = threading.Thread(target=_quietly, args=(eng.self_loop_rows,)) if A.nnz >= _SIDE_THREAD_MIN_NNZ else None
+        if side:
+            side.start()
         try:
             eng.extract(rule, rho_eff, epsilon); t.append(time.perf_counter())
             eng.assemble(); t.append(time.perf_counter())
         finally:
-            side.join()
+            if side:
+                side.join()
         X = eng.features(); t.append(time.perf_counter())
         if os.environ.get("ARCTE_CUDA_DEBUG"):
             import sys
