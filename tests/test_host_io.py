@@ -275,3 +275,53 @@ def test_ones_mapping_is_ordinary_writable_memory():
     small = hostmem.ones(100)
     assert isinstance(small, np.ndarray) and small.sum() == 100.0
     del a, b
+
+
+def test_arcte_single_gpu_host_flow_with_a_fake_engine(monkeypatch):
+    """Order of the library calls behind arcte() on one GPU, and the side thread that finds the self-loop rows
+    while the device walks: started only for large inputs, always joined before features()."""
+    import threading
+    import reveal_graph_embedding_b200.embedding.arcte.arcte as mod
+
+    class FakeEngine:
+        def __init__(self):
+            self.calls, self.loop_threads = [], []
+
+        def set_graph(self, A, canonical=False):
+            self.calls.append("set_graph")
+
+        def self_loop_rows(self):
+            self.loop_threads.append(threading.current_thread() is threading.main_thread())
+
+        def extract(self, rule, rho, eps):
+            self.calls.append("extract")
+
+        def assemble(self):
+            self.calls.append("assemble")
+
+        def features(self):
+            self.calls.append("features")
+            return "X"
+
+    A = sparse.csr_matrix(np.array([[0.0, 1.0], [1.0, 0.0]]))
+    for min_nnz, threaded in ((1 << 20, False), (1, True)):
+        eng = FakeEngine()
+        monkeypatch.setattr(mod, "get_engine", lambda d=0, e=eng: e)
+        monkeypatch.setattr(mod, "device_count", lambda: 1)
+        monkeypatch.setattr(mod, "_SIDE_THREAD_MIN_NNZ", min_nnz)
+        assert mod.arcte(A, 0.1, 1e-5) == "X"
+        assert eng.calls == ["set_graph", "extract", "assemble", "features"]
+        assert eng.loop_threads == ([False] if threaded else [])   # ran off the main thread, or not at all here
+
+    # a failing extract still joins the thread and propagates
+    class Failing(FakeEngine):
+        def extract(self, rule, rho, eps):
+            raise RuntimeError("boom")
+    eng = Failing()
+    monkeypatch.setattr(mod, "get_engine", lambda d=0, e=eng: e)
+    monkeypatch.setattr(mod, "_SIDE_THREAD_MIN_NNZ", 1)
+    import pytest
+    with pytest.raises(RuntimeError, match="boom"):
+        mod.arcte(A, 0.1, 1e-5)
+    assert threading.active_count() == 1 or all(not t.name.startswith("Thread-") or not t.is_alive()
+                                                 for t in threading.enumerate() if t is not threading.main_thread())
