@@ -130,3 +130,124 @@ def test_row_blocks_partition_the_rows_and_match_the_device_rule():
                                              np.random.default_rng(n + G).integers(0, n, 200)]))
             for x in rows:
                 assert dest_of(int(x), n, G) == owner[x]
+
+
+# ------------------------------------------------------------------------------------------------
+# arcte_distributed() end to end on CPU: the host flow of one rank (side thread for the self-loop rows, size
+# exchange, both ways home, patching of the 2.0 diagonals) around an engine whose device work is done by the oracle
+# ------------------------------------------------------------------------------------------------
+def _oracle_engine(rank, world):
+    from oracle import arcte_oracle as O
+    from reveal_graph_embedding_b200 import distributed as ardist
+    from reveal_graph_embedding_b200.engine import Engine, host_write_to
+
+    class OracleEngine(Engine):   # patch_self_loops / self_loop_rows are the product's own (pure numpy)
+        def __init__(self):
+            self._values_structural = True
+            self.calls = []
+
+        def set_graph(self, A, canonical=False):
+            self.A, self.n, self.nnz, self._loops = A, int(A.shape[0]), int(A.nnz), None
+            self._indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+            self._indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+            self.calls.append("set_graph")
+
+        def comm_info(self):
+            return (world, rank, 0)
+
+        def extract(self, rule, rho, eps, shard_rank=0, shard_count=1):
+            assert (shard_rank, shard_count) == (rank, world)
+            self.rule, self.rho, self.eps = rule, rho, eps
+            self.calls.append("extract")
+
+        def exchange_assemble(self):
+            g = O.Graph(self.A)
+            seeds = g.seeds()
+            sds, segs, mems = [], [], []
+            for r in range(world):   # what the all-to-all delivers: every shard's communities
+                mine = seeds[list(ardist.shard_positions(seeds.size, r, world))]
+                sd, seg, mem, eff, st = O.extract(g, self.rule, self.rho, self.eps, mine, 1)
+                sds.append(sd), segs.append(seg), mems.append(mem)
+            X = O.assemble(g, np.concatenate(sds), np.concatenate(segs), np.concatenate(mems))
+            lo, hi = ardist.row_range(self.n, rank, world)
+            self.blk = X[lo:hi].tocsr()
+            self.out_nnz, self.out_rows = int(self.blk.nnz), hi - lo
+            self.calls.append("exchange_assemble")
+            return self.out_nnz
+
+        def fetch_block(self, indptr, indices, data, values_are_ones=False, n_threads=0):
+            if indptr is not None:
+                indptr[:] = self.blk.indptr
+            if indices is not None:
+                indices[:] = self.blk.indices
+            if data is not None:
+                data[:] = 1.0 if values_are_ones else self.blk.data
+
+        def fetch_block_to(self, pid, a_ip, a_idx, a_dat, values_are_ones=False, n_threads=0):
+            assert not a_ip and not a_dat   # structural result: only the column indices travel
+            host_write_to(pid, a_idx, self.blk.indices.astype(np.int32))
+
+    return OracleEngine()
+
+
+def _dist_worker(rank, world, port, name, out_dir, no_remote, everywhere):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if no_remote:
+        os.environ["ARCTE_CUDA_NO_REMOTE_WRITES"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import EPS, RHO, load_golden
+        from reveal_graph_embedding_b200 import distributed as ardist
+        A, z = load_golden(name)
+        eng = _oracle_engine(rank, world)
+        X = ardist.arcte_distributed(A, 0, RHO, EPS, engine=eng, all_ranks=everywhere)
+        assert eng.calls == ["set_graph", "extract", "exchange_assemble"]
+        assert eng._loops is not None          # found by the side thread (or, failing that, by the patch)
+        if rank == 0 or everywhere:
+            np.savez(os.path.join(out_dir, "rank%d.npz" % rank), indptr=X.indptr, indices=X.indices, data=X.data)
+        else:
+            assert X is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name,no_remote,everywhere",
+                         [(2, "edgecases160", False, False), (3, "edgecases160", True, False),
+                          (2, "ba300", False, True), (3, "planted419", False, False)])
+def test_arcte_distributed_host_flow_with_an_oracle_engine(tmp_path, world, name, no_remote, everywhere):
+    """edgecases160 has self loops: the 2.0 diagonals are patched into a value array of ones on the way home."""
+    from helpers import golden_features, load_golden
+    port = _free_port()
+    mp.spawn(_dist_worker, args=(world, port, name, str(tmp_path), no_remote, everywhere), nprocs=world, join=True)
+    A, z = load_golden(name)
+    want = golden_features(z, 0, A.shape[0])
+    ranks = range(world) if everywhere else [0]
+    for r in ranks:
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        assert np.array_equal(got["indptr"], want.indptr)
+        assert np.array_equal(got["indices"], want.indices)
+        assert np.array_equal(got["data"], want.data)
+
+
+@pytest.mark.parametrize("n_gpus,name", [(2, "edgecases160"), (3, "ba300")])
+def test_in_process_multi_gpu_host_flow_with_oracle_engines(monkeypatch, n_gpus, name):
+    """One process driving several GPUs (embedding/arcte/arcte.py): per-GPU threads, one self-loop scan shared by
+    all engines, every engine's row block fetched into its slice of the result, 2.0 diagonals patched per block."""
+    from helpers import EPS, RHO, golden_features, load_golden
+    import reveal_graph_embedding_b200.embedding.arcte.arcte as mod
+    engines = [_oracle_engine(r, n_gpus) for r in range(n_gpus)]
+    scans = []
+    for e in engines:
+        real = e.self_loop_rows
+        e.self_loop_rows = (lambda real=real, e=e: (scans.append(1) if e._loops is None else None, real())[1])
+    monkeypatch.setattr(mod, "get_engine", lambda d=0: engines[d])
+    monkeypatch.setattr(mod, "device_count", lambda: n_gpus)
+    monkeypatch.setattr(mod.Engine, "comm_init_all", staticmethod(lambda engs: None))
+    A, z = load_golden(name)
+    X = mod.arcte(A, RHO, EPS)
+    want = golden_features(z, 0, A.shape[0])
+    assert np.array_equal(X.indptr, want.indptr) and np.array_equal(X.indices, want.indices)
+    assert np.array_equal(X.data, want.data)
+    assert all(e.calls == ["set_graph", "extract", "exchange_assemble"] for e in engines)
+    assert len(scans) == 1 and all(e._loops is engines[0]._loops for e in engines)   # scanned once, shared
