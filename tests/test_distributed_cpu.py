@@ -136,6 +136,9 @@ def test_row_blocks_partition_the_rows_and_match_the_device_rule():
 # arcte_distributed() end to end on CPU: the host flow of one rank (side thread for the self-loop rows, size
 # exchange, both ways home, patching of the 2.0 diagonals) around an engine whose device work is done by the oracle
 # ------------------------------------------------------------------------------------------------
+_ORACLE_LOCK = __import__("threading").Lock()   # the oracle library is not re-entrant; the in-process path calls from threads
+
+
 def _oracle_engine(rank, world):
     from oracle import arcte_oracle as O
     from reveal_graph_embedding_b200 import distributed as ardist
@@ -161,6 +164,10 @@ def _oracle_engine(rank, world):
             self.calls.append("extract")
 
         def exchange_assemble(self):
+            with _ORACLE_LOCK:
+                return self._exchange_assemble()
+
+        def _exchange_assemble(self):
             g = O.Graph(self.A)
             seeds = g.seeds()
             sds, segs, mems = [], [], []
