@@ -147,7 +147,7 @@ int exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, DevBuf &scrat
 // The scatter kernel first REORDERS the tile in shared memory (digit-major, tile order kept
 // inside a digit) and then writes it out front to back: consecutive threads write consecutive
 // addresses of one digit's global run, whole sectors at a time.  (Round 1 let every lane store
-// its pair straight to its own global position: 510 GB/s on 517 M pairs, profiles/r2_k5_sort.md.)
+// its pair straight to its own global position: 510 GB/s on 517 M pairs)
 // ------------------------------------------------------------------------------------
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;
